@@ -1,0 +1,170 @@
+"""Generate golden fixtures by running the reference's OWN Python sources.  TEST INFRASTRUCTURE.
+
+Runs only in the build container (needs /root/reference).  The reference package cannot be
+imported whole (mpi4py / h5py / matplotlib / cupy are absent), so its unmodified
+``pyLOM/vmmath/{maths,averaging,truncation,svd,stats}.py`` and ``pyLOM/POD/wrapper.py`` are
+loaded by file path under a stub ``pyLOM.utils`` (numpy aliased as ``cp`` exactly like
+``pyLOM/utils/gpu.py:66`` does without cupy; ``mpi_send/mpi_recv`` backed by per-pair queues;
+one *thread* per simulated rank, each with its own module instances because
+``MPI_RANK/MPI_SIZE`` are bound at import time, ``pyLOM/vmmath/svd.py:14``).
+
+Usage:  python oracle/gen_golden.py            -> writes tests/golden/*.npz
+"""
+import importlib.util, os, queue, sys, threading, types
+import numpy as np
+
+REF = os.environ.get("PYLOM_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import synth  # noqa: E402
+
+
+class _World:
+    def __init__(self, size):
+        self.size = size
+        self.q = {(s, d): queue.Queue() for s in range(size) for d in range(size)}
+        self.red = threading.Barrier(size)
+        self.slots = [None] * size
+
+
+def _load_rank(world, rank):
+    """Return a namespace with the reference functions bound to (rank, world.size)."""
+    tag = f"pyLOMref_r{rank}_of{world.size}_{id(world)}"
+    def mod(name, path=False):
+        m = types.ModuleType(name)
+        if path:
+            m.__path__ = []
+        sys.modules[name] = m
+        return m
+    pk = mod(tag, True)
+    utils = mod(tag + ".utils", True)
+    gpu = mod(tag + ".utils.gpu")
+    cr = mod(tag + ".utils.cr")
+    vm = mod(tag + ".vmmath", True)
+    pod = mod(tag + ".POD", True)
+    gpu.cp = np
+    gpu.gpu_to_cpu = lambda x: x
+    gpu.cpu_to_gpu = lambda x: x
+    ident = lambda name: (lambda f: f)
+    cr.cr_nvtx = ident
+    cr.cr_start = lambda *a, **k: None
+    cr.cr_stop = lambda *a, **k: None
+    def send(obj, dest):
+        world.q[(rank, dest)].put(np.array(obj, copy=True))
+    def recv(source=0):
+        return world.q[(source, rank)].get()
+    def reduce(x, root=0, op="sum", all=False):
+        world.slots[rank] = np.array(x, copy=True)
+        world.red.wait()
+        tot = sum(world.slots[1:], world.slots[0].copy())
+        world.red.wait()
+        return tot
+    utils.cr_nvtx = ident
+    utils.MPI_RANK, utils.MPI_SIZE = rank, world.size
+    utils.mpi_send, utils.mpi_recv, utils.mpi_reduce = send, recv, reduce
+    utils.gpu, utils.cr = gpu, cr
+    utils.gpu_to_cpu, utils.cpu_to_gpu = gpu.gpu_to_cpu, gpu.cpu_to_gpu
+    def load(sub, rel):
+        spec = importlib.util.spec_from_file_location(f"{tag}.{sub}", os.path.join(REF, "pyLOM", rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = m
+        spec.loader.exec_module(m)
+        return m
+    out = types.SimpleNamespace()
+    for name in ("maths", "averaging", "truncation", "stats", "svd"):
+        m = load(f"vmmath.{name}", f"vmmath/{name}.py")
+        for k, v in vars(m).items():
+            if callable(v) and not k.startswith("_"):
+                setattr(vm, k, v)
+        setattr(out, name, m)
+    out.POD = load("POD.wrapper", "POD/wrapper.py")
+    return out
+
+
+def run_ranks(fn, shards):
+    """Run ``fn(ref_namespace, shard)`` on len(shards) simulated ranks; return list of results."""
+    P = len(shards)
+    world = _World(P)
+    refs = [_load_rank(world, r) for r in range(P)]
+    res, err = [None] * P, []
+    def work(r):
+        try:
+            res[r] = fn(refs[r], shards[r])
+        except Exception as e:  # pragma: no cover
+            err.append((r, e))
+    th = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if err:
+        raise err[0][1]
+    return res
+
+
+def split_rows(A, P):
+    sys.path.insert(0, HERE)
+    from pod_oracle import worksplit
+    return [A[slice(*worksplit(0, A.shape[0], r, P))] for r in range(P)]
+
+
+CASES = [
+    # name, m, n, kind, seed, ranks
+    ("ex4x2", 4, 2, "example_svd", 0, (1,)),            # Examples/example_SVD.py:17
+    ("rand_300x8", 300, 8, "rand", 11, (1, 2, 3, 4)),
+    ("synth_700x24", 700, 24, "synth", 2021, (1, 2, 4)),
+    ("cond_640x33", 640, 33, "cond1e9", 7, (1, 3, 8)),
+    ("cyl_twin_400x151", 400, 151, "synth", 2021, (1, 2)),   # cfg1 twin (n=151)
+]
+
+
+def make_input(m, n, kind, seed):
+    if kind == "example_svd":
+        return np.array([[1, 2], [3, 4], [5, 6], [7, 8]], dtype=np.double, order="C")
+    if kind == "rand":
+        return synth.random_matrix(m, n, seed)
+    if kind == "cond1e9":
+        return synth.random_matrix(m, n, seed, cond=1e9)
+    return synth.snapshots(m, n, seed)
+
+
+def main():
+    outdir = os.path.join(HERE, "..", "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    for name, m, n, kind, seed, ranks in CASES:
+        A = make_input(m, n, kind, seed)
+        blob = {"A": A}
+        for P in ranks:
+            shards = split_rows(A, P)
+            r = run_ranks(lambda ref, Ai: ref.svd.tsqr_svd(Ai), shards)
+            blob[f"tsqr_svd_P{P}_U"] = np.vstack([x[0] for x in r])
+            blob[f"tsqr_svd_P{P}_S"] = r[0][1]
+            blob[f"tsqr_svd_P{P}_V"] = r[0][2]
+            for x in r[1:]:
+                assert np.array_equal(x[1], r[0][1]), "S differs across ranks"
+            def pod(ref, Xi):
+                U, S, V = ref.POD.run(Xi, remove_mean=True)
+                Ur, Sr, Vr = ref.POD.truncate(U, S, V, r=1e-6)
+                Xr = ref.POD.reconstruct(Ur, Sr, Vr)
+                mean = ref.averaging.temporal_mean(Xi)
+                Y = ref.averaging.subtract_mean(Xi, mean)
+                rm = ref.stats.RMSE(Y, Xr)
+                return U, S, V, Sr.shape[0], Xr, mean, rm
+            r = run_ranks(pod, shards)
+            blob[f"pod_P{P}_U"] = np.vstack([x[0] for x in r])
+            blob[f"pod_P{P}_S"] = r[0][1]
+            blob[f"pod_P{P}_V"] = r[0][2]
+            blob[f"pod_P{P}_N"] = np.array(r[0][3])
+            blob[f"pod_P{P}_Xrec"] = np.vstack([x[4] for x in r])
+            blob[f"pod_P{P}_mean"] = np.concatenate([x[5] for x in r])
+            blob[f"pod_P{P}_rmse"] = np.array(float(r[0][6]))
+        # truncation rule probes on the P=1 spectrum
+        ref = _load_rank(_World(1), 0)
+        S = blob["tsqr_svd_P1_S"]
+        blob["trunc_r"] = np.array([1e-8, 1e-3, 0.5, -0.9, -0.5, -1.0])
+        blob["trunc_N"] = np.array([ref.truncation.compute_truncation_residual(S, r) for r in blob["trunc_r"]])
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, {k: v.shape for k, v in blob.items() if k.endswith("_S")}, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,283 @@
+"""CPU oracle for the POD / TSQR-SVD hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This is a numpy restatement of the reference algorithm (pyLOM 3.2.8).  It is the
+*checker* for the CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
+package (``pyloworder_b200``) never imports anything from ``oracle/``.
+
+Parity status: PINNED.  ``oracle/gen_golden.py`` runs the reference's own unmodified
+``pyLOM/vmmath/{maths,averaging,truncation,svd,stats}.py`` and ``pyLOM/POD/wrapper.py``
+(loaded under a stub ``pyLOM.utils``; P simulated ranks) and stores inputs/outputs under
+``tests/golden/``; ``tests/test_oracle.py`` checks every function here against those
+fixtures, and (when built) against ``oracle/_ref/libpylom_ref.so`` compiled from the
+reference's C sources.
+
+Third-party arithmetic: the reference delegates QR/SVD/GEMM to LAPACK/BLAS
+(OpenBLAS 0.3.17 or oneMKL 2024.2.0.634, ``options.cfg:45-46``) or numpy; here it is
+numpy's bundled OpenBLAS.  LAPACK results are unique only up to the sign of each mode
+(and rotation inside degenerate clusters), so all comparisons are sign-invariant.
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------------------
+# partitioning
+# --------------------------------------------------------------------------------------
+def worksplit(istart: int, iend: int, whoAmI: int, nWorkers: int):
+    """Contiguous row range of worker ``whoAmI``  (pyLOM/utils/parall.py:24-48)."""
+    istart_l, iend_l = istart, iend
+    irange = iend - istart
+    if nWorkers < irange:
+        rangePerProcess = int(np.floor(irange / nWorkers))
+        istart_l = istart + whoAmI * rangePerProcess
+        iend_l = istart_l + rangePerProcess
+        remainder = irange - rangePerProcess * nWorkers
+        if remainder > whoAmI:
+            istart_l += whoAmI
+            iend_l += whoAmI + 1
+        else:
+            istart_l += remainder
+            iend_l += remainder
+    else:
+        istart_l = whoAmI if whoAmI < iend else iend
+        iend_l = whoAmI + 1 if whoAmI < iend else iend
+    return istart_l, iend_l
+
+
+# --------------------------------------------------------------------------------------
+# averaging
+# --------------------------------------------------------------------------------------
+def temporal_mean(X: np.ndarray) -> np.ndarray:
+    """Row mean over the n snapshots (pyLOM/vmmath/averaging.py:17-29, src/averaging.c:29-46)."""
+    return np.mean(X, axis=1)
+
+
+def subtract_mean(X: np.ndarray, X_mean: np.ndarray) -> np.ndarray:
+    """out[i,j] = X[i,j] - X_mean[i] (pyLOM/vmmath/averaging.py:31-44, src/averaging.c:109-124)."""
+    return X - X_mean[:, None]
+
+
+# --------------------------------------------------------------------------------------
+# small dense algebra
+# --------------------------------------------------------------------------------------
+def matmul(A, B):
+    """C = A x B (pyLOM/vmmath/maths.py:76-90, src/vector_matrix.c:234-242)."""
+    return np.matmul(A, B)
+
+
+def vecmat(v, A):
+    """C[i,:] = v[i]*A[i,:] (pyLOM/vmmath/maths.py:112-129, src/vector_matrix.c:401-414)."""
+    return v[:, None] * A
+
+
+def qr(A):
+    """Thin Householder QR (pyLOM/vmmath/svd.py:28-36; geqrf+orgqr in src/svd.c:280-321)."""
+    return np.linalg.qr(A)
+
+
+def svd(A):
+    """Thin SVD, S descending, V returned as V^T (pyLOM/vmmath/svd.py:38-47, src/svd.c:83-139)."""
+    return np.linalg.svd(A, full_matrices=False)
+
+
+def next_power_of_2(n: int) -> int:
+    """pyLOM/vmmath/svd.py:17-25, src/svd.c:409-414."""
+    p = 1
+    if n and not (n & (n - 1)):
+        return n
+    while p < n:
+        p <<= 1
+    return p
+
+
+# --------------------------------------------------------------------------------------
+# TSQR (butterfly, P simulated ranks in one process)
+# --------------------------------------------------------------------------------------
+def tsqr(A_list):
+    """Parallel QR of a row-partitioned matrix, P = len(A_list) ranks.
+
+    Follows pyLOM/vmmath/svd.py:49-118 (src/svd.c:565-676) step by step; every rank's
+    control flow is executed level-synchronously, a send/recv pair becomes a mailbox
+    hand-off.  Returns ([Q_i], [R_i]) -- R is identical on every rank.
+    """
+    P = len(A_list)
+    n = A_list[0].shape[1]
+    dt = A_list[0].dtype
+    nextPower = next_power_of_2(P)
+    nlevels = int(np.log2(nextPower))
+    Q1 = [None] * P
+    R = [None] * P
+    for r in range(P):
+        Q1[r], R[r] = qr(A_list[r])                                   # svd.py:60
+    QW = [np.eye(n, dtype=dt) for _ in range(P)]                      # svd.py:63
+    C = [np.zeros((2 * n, n), dt) for _ in range(P)]
+    Q2l = [np.zeros((2 * n * nlevels, n), dt) for _ in range(P)]
+    blevel = 1
+    for ilevel in range(nlevels):                                     # svd.py:67-84
+        mailbox = {}
+        for r in range(P):
+            C[r][:n, :] = R[r]
+            prank = r ^ blevel
+            if r & blevel and prank < P:
+                mailbox[prank] = R[r].copy()                          # mpi_send(R, prank)
+        for r in range(P):
+            prank = r ^ blevel
+            if not (r & blevel) and prank < P:
+                R[r] = mailbox[r]                                     # mpi_recv
+                C[r][n:, :] = R[r]
+                Q2i, R[r] = qr(C[r])
+                Q2l[r][2 * n * ilevel:2 * n * ilevel + 2 * n, :] = Q2i
+        blevel <<= 1
+    if P > 1:                                                         # svd.py:87-115
+        blevel = 1 << (nlevels - 1)
+        mask = blevel - 1
+    for ilevel in reversed(range(nlevels)):
+        mailbox = {}
+        Q2i_of = {}
+        for r in range(P):                                            # senders first
+            if r & mask == 0:
+                Cb = Q2l[r][2 * n * ilevel:2 * n * ilevel + 2 * n, :]
+                Q2i = matmul(Cb, QW[r])
+                Q2i_of[r] = Q2i
+                prank = r ^ blevel
+                if not (r & blevel) and prank < P:
+                    msg = np.empty((2 * n, n), dt)
+                    msg[:n, :] = R[r]
+                    msg[n:, :] = Q2i[n:, :]
+                    QW[r] = Q2i[:n, :].copy()
+                    mailbox[prank] = msg
+        for r in range(P):                                            # then receivers
+            if r & mask == 0:
+                prank = r ^ blevel
+                if r & blevel and prank < P:
+                    msg = mailbox[r]
+                    R[r] = msg[:n, :].copy()
+                    QW[r] = msg[n:, :].copy()
+        blevel >>= 1
+        mask >>= 1
+    Q = [matmul(Q1[r], QW[r]) for r in range(P)]                      # svd.py:117
+    return Q, R
+
+
+def tsqr_svd(A_list):
+    """TSQR-based SVD on P simulated ranks (pyLOM/vmmath/svd.py:227-252, src/svd.c:678-712).
+
+    Accepts a single 2-D array (one rank) or a list of row blocks.  Returns
+    ([U_i], S, V) with V = V^T (n x n).
+    """
+    single = isinstance(A_list, np.ndarray)
+    if single:
+        A_list = [A_list]
+    Q, R = tsqr(A_list)
+    Ur, S, V = svd(R[0])
+    U = [matmul(Qi, Ur) for Qi in Q]
+    return (U[0] if single else U), S, V
+
+
+# --------------------------------------------------------------------------------------
+# POD
+# --------------------------------------------------------------------------------------
+def pod_run(X_list, remove_mean: bool = True):
+    """POD.run on P simulated ranks (pyLOM/POD/wrapper.py:16-51).  ``X_list`` may be a
+    single array.  divide_variance / randomized are outside the hot path."""
+    single = isinstance(X_list, np.ndarray)
+    Xs = [X_list] if single else X_list
+    if remove_mean:
+        Ys = [subtract_mean(X, temporal_mean(X)) for X in Xs]
+    else:
+        Ys = [X.copy() for X in Xs]
+    U, S, V = tsqr_svd(Ys)
+    return (U[0] if single else U), S, V
+
+
+def vector_norm(v, start=0):
+    """pyLOM/vmmath/maths.py:47-59."""
+    return np.linalg.norm(v[start:], 2)
+
+
+def vector_sum(v, start=0):
+    """pyLOM/vmmath/maths.py:32-44."""
+    return np.sum(v[start:])
+
+
+def compute_truncation_residual(S, r):
+    """Number of modes to keep (pyLOM/vmmath/truncation.py:17-39, src/truncation.c:46-74)."""
+    N = 0
+    if r > 0:
+        normS = vector_norm(S, 0)
+        for ii in range(S.shape[0]):
+            accumulative = vector_norm(S, ii) / normS
+            if accumulative < r:
+                break
+            N += 1
+    else:
+        r = abs(r)
+        normS = vector_sum(S, 0)
+        accumulative = 0
+        for ii in range(S.shape[0]):
+            accumulative += S[ii] / normS
+            N += 1
+            if accumulative > r:
+                break
+    return N
+
+
+def truncate(U, S, V, r=1e-8):
+    """pyLOM/POD/wrapper.py:55-82."""
+    N = int(r) if r >= 1 else compute_truncation_residual(S, r)
+    return U[:, :N], S[:N], V[:N, :]
+
+
+def reconstruct(U, S, V):
+    """X = U diag(S) V (pyLOM/POD/wrapper.py:86-103); the mean is NOT re-added."""
+    return matmul(U, vecmat(S, V))
+
+
+def RMSE(A_list, B_list, relative: bool = True):
+    """sqrt(sum((A-B)^2)/sum(A^2)) with both sums reduced over ranks (pyLOM/vmmath/stats.py:17-34)."""
+    if isinstance(A_list, np.ndarray):
+        A_list, B_list = [A_list], [B_list]
+    s1 = sum(float(np.sum((A - B) * (A - B))) for A, B in zip(A_list, B_list))
+    if relative:
+        s2 = sum(float(np.sum(A * A)) for A in A_list)
+    else:
+        s2 = float(np.prod(np.sum([np.array(A.shape) for A in A_list], axis=0)))
+    return np.sqrt(s1 / s2)
+
+
+# --------------------------------------------------------------------------------------
+# sign-/rotation-invariant comparators used by the parity tests
+# --------------------------------------------------------------------------------------
+def compare_svd(U_ref, S_ref, V_ref, U, S, V, gap_tol=1e-6, floor=1e-8):
+    """Return a dict of parity metrics (SURVEY.md section 8d acceptance).
+
+    * ``sigma_rel``  max_k |s_k - s_k_ref| / s_1_ref
+    * ``sigma_rel_each`` max over k with s_k/s_1 >= 1e-6 of |s_k - s_k_ref|/s_k_ref
+    * ``mode_min``   min over well separated modes of |<u_ref_k, u_k>|
+    * ``vmode_min``  same for rows of V
+    """
+    S_ref = np.asarray(S_ref); S = np.asarray(S)
+    s1 = S_ref[0]
+    out = {"sigma_rel": float(np.max(np.abs(S - S_ref)) / s1)}
+    big = S_ref / s1 >= 1e-6
+    out["sigma_rel_each"] = float(np.max(np.abs(S[big] - S_ref[big]) / S_ref[big])) if big.any() else 0.0
+    n = S_ref.shape[0]
+    sep = np.zeros(n, bool)
+    for k in range(n):
+        lo = S_ref[k - 1] - S_ref[k] if k > 0 else np.inf
+        hi = S_ref[k] - S_ref[k + 1] if k < n - 1 else np.inf
+        sep[k] = (min(lo, hi) / s1 >= gap_tol) and (S_ref[k] / s1 >= floor)
+    out["n_separated"] = int(sep.sum())
+    if sep.any():
+        du = np.abs(np.einsum("ik,ik->k", U_ref[:, sep], U[:, sep]))
+        dv = np.abs(np.einsum("ki,ki->k", V_ref[sep, :], V[sep, :]))
+        out["mode_min"] = float(du.min())
+        out["vmode_min"] = float(dv.min())
+    else:
+        out["mode_min"] = out["vmode_min"] = 1.0
+    return out

@@ -1,0 +1,113 @@
+"""Pin the numpy oracle (oracle/pod_oracle.py) against (1) the golden vectors produced by the
+reference's own Python sources (oracle/gen_golden.py) and (2) the reference's own C sources
+compiled into oracle/_ref/libpylom_ref.so.  CPU only."""
+import ctypes, glob, os
+import numpy as np
+import pytest
+
+import pod_oracle as po
+import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _split(A, P):
+    return [A[slice(*po.worksplit(0, A.shape[0], r, P))] for r in range(P)]
+
+
+def test_have_goldens():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_tsqr_svd_matches_reference_python(path):
+    g = np.load(path)
+    A = g["A"]
+    for key in [k for k in g.files if k.startswith("tsqr_svd_P") and k.endswith("_S")]:
+        P = int(key.split("_P")[1].split("_")[0])
+        U, S, V = po.tsqr_svd(_split(A, P))
+        U = np.vstack(U)
+        m = po.compare_svd(g[f"tsqr_svd_P{P}_U"], g[key], g[f"tsqr_svd_P{P}_V"], U, S, V)
+        assert m["sigma_rel"] <= 1e-13, (P, m)
+        assert m["mode_min"] >= 1 - 1e-10 and m["vmode_min"] >= 1 - 1e-10, (P, m)
+        # the oracle is the same LAPACK calls in the same order: expect bitwise S
+        assert np.array_equal(S, g[key]), P
+        assert np.abs(U.T @ U - np.eye(A.shape[1])).max() < 1e-13
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_pod_matches_reference_python(path):
+    g = np.load(path)
+    A = g["A"]
+    for key in [k for k in g.files if k.startswith("pod_P") and k.endswith("_S")]:
+        P = int(key.split("_P")[1].split("_")[0])
+        shards = _split(A, P)
+        U, S, V = po.pod_run(shards, remove_mean=True)
+        assert np.allclose(S, g[key], rtol=0, atol=1e-13 * g[key][0])
+        mean = np.concatenate([po.temporal_mean(X) for X in shards])
+        assert np.array_equal(mean, g[f"pod_P{P}_mean"])
+        Uc = np.vstack(U)
+        Ur, Sr, Vr = po.truncate(Uc, S, V, r=1e-6)
+        assert Sr.shape[0] == int(g[f"pod_P{P}_N"])
+        Xr = po.reconstruct(Ur, Sr, Vr)
+        assert np.abs(Xr - g[f"pod_P{P}_Xrec"]).max() <= 1e-12 * np.abs(A).max()
+        Y = np.vstack([po.subtract_mean(X, po.temporal_mean(X)) for X in shards])
+        assert abs(po.RMSE(Y, Xr) - float(g[f"pod_P{P}_rmse"])) <= 1e-12
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_truncation_rule(path):
+    g = np.load(path)
+    S = g["tsqr_svd_P1_S"]
+    for r, N in zip(g["trunc_r"], g["trunc_N"]):
+        assert po.compute_truncation_residual(S, float(r)) == int(N)
+
+
+def test_worksplit_covers_range():
+    for m, P in ((10, 3), (89351, 8), (7, 7), (5, 8), (1000, 1)):
+        edges = [po.worksplit(0, m, r, P) for r in range(P)]
+        assert edges[0][0] == 0
+        for a, b in zip(edges[:-1], edges[1:]):
+            assert a[1] == b[0] or m <= P
+        assert max(e[1] for e in edges) == m
+
+
+def test_synth_slices_reproducible():
+    X = synth.snapshots(1000, 16, 2021)
+    assert np.array_equal(X[300:450], synth.snapshots(1000, 16, 2021, 300, 450))
+    assert np.linalg.matrix_rank(X) == 16
+
+
+# ---- the reference's own C sources -------------------------------------------------------------
+REFLIB = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libpylom_ref.so")
+needs_ref = pytest.mark.skipif(not os.path.exists(REFLIB), reason="oracle/_ref not built (make -C oracle ref)")
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+@needs_ref
+def test_oracle_vs_reference_c_tsqr_svd():
+    lib = ctypes.CDLL(REFLIB)
+    for m, n, seed in ((500, 12, 3), (2000, 64, 4), (1800, 151, 2021)):
+        A = synth.snapshots(m, n, seed) if n == 151 else synth.random_matrix(m, n, seed, cond=1e6)
+        U = np.zeros((m, n)); S = np.zeros(n); V = np.zeros((n, n))
+        info = lib.dtsqr_svd(_p(U), _p(S), _p(V), _p(A.copy()), ctypes.c_int(m), ctypes.c_int(n))
+        assert info == 0
+        Uo, So, Vo = po.tsqr_svd(A)
+        mtr = po.compare_svd(U, S, V, Uo, So, Vo)
+        assert mtr["sigma_rel"] <= 1e-13 and mtr["sigma_rel_each"] <= 1e-9, mtr
+        assert mtr["mode_min"] >= 1 - 1e-9, mtr
+
+
+@needs_ref
+def test_oracle_vs_reference_c_averaging():
+    lib = ctypes.CDLL(REFLIB)
+    X = synth.snapshots(777, 37, 5)
+    mean = np.zeros(777); Y = np.zeros_like(X)
+    lib.dtemporal_mean(_p(mean), _p(X), ctypes.c_int(777), ctypes.c_int(37))
+    lib.dsubtract_mean(_p(Y), _p(X), _p(mean), ctypes.c_int(777), ctypes.c_int(37))
+    assert np.abs(mean - po.temporal_mean(X)).max() <= 4e-16 * np.abs(X).max() * 37
+    assert np.abs(Y - po.subtract_mean(X, mean)).max() == 0.0

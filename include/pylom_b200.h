@@ -1,0 +1,95 @@
+/* libpylom_b200 -- C ABI of the B200-native POD / TSQR-SVD hot path.
+ *
+ * Drop-in boundary for pyLOM's compiled math layer (pyLOM/vmmath/src/{averaging,svd,vector_matrix,
+ * stats}.h as declared to Cython in pyLOM/vmmath/cfuncs.pxd).  Every entry point names the
+ * reference function it replaces.  Differences from the reference ABI, all deliberate:
+ *   - sizes are int64_t (the reference's `int m*n` overflows at 2^31 elements, svd.c:586,697);
+ *   - array arguments are DEVICE pointers unless the name ends in `_host`;
+ *   - no hidden malloc on the device: the caller passes a workspace sized by the matching
+ *     *_workspace_bytes() query (the reference mallocs/frees scratch inside each call);
+ *   - explicit stream (a cudaStream_t passed as void*); calls are stream ordered;
+ *   - return value 0 = ok, < 0 = bad argument (minus its position), > 0 = CUDA / convergence error;
+ *     pl_last_error() returns the message (the reference returns the LAPACK info, svd.pyx:399).
+ * Matrices are row-major, contiguous, fp64, exactly as in the reference (C order numpy arrays).
+ */
+#ifndef PYLOM_B200_H
+#define PYLOM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int pl_version(void);
+const char* pl_last_error(void);
+
+/* ---- averaging:  pyLOM/vmmath/src/averaging.h ------------------------------------------------ */
+/* replaces dtemporal_mean(double *out, double *X, const int m, const int n)   averaging.c:29-46  */
+int pl_temporal_mean_f64(double* out, const double* X, int64_t m, int64_t n, void* stream);
+/* replaces dsubtract_mean(double *out, double *X, double *X_mean, m, n)       averaging.c:109-124 */
+int pl_subtract_mean_f64(double* out, const double* X, const double* X_mean, int64_t m, int64_t n, void* stream);
+/* fused temporal_mean + subtract_mean (what POD.run does back to back, POD/wrapper.pyx:127-133) */
+int pl_center_f64(double* Y, double* X_mean, const double* X, int64_t m, int64_t n, void* stream);
+
+/* ---- dense helpers:  pyLOM/vmmath/src/vector_matrix.h ---------------------------------------- */
+/* replaces dmatmul(double *C, double *A, double *B, m, n, k): C(m,n) = A(m,k) B(k,n)  vector_matrix.c:234-242.
+ * lda/ldc allow the strided views POD.truncate returns (POD/wrapper.py:78-80). */
+size_t pl_matmul_workspace_bytes(int64_t n, int64_t k);
+int pl_matmul_f64(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                  int64_t m, int64_t n, int64_t k, void* ws, size_t ws_bytes, void* stream);
+/* replaces dvecmat(double *v, double *A, m, n): C[i,:] = v[i] A[i,:] (out of place)  vector_matrix.c:401-414 */
+int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream);
+
+/* ---- statistics:  pyLOM/vmmath/src/stats.h --------------------------------------------------- */
+/* the two local sums of dRMSE_relative (stats.c:44-72): out2[0] = sum (A-B)^2, out2[1] = sum A^2.
+ * ws: >= pl_rmse_workspace_bytes() */
+size_t pl_rmse_workspace_bytes(void);
+int pl_rmse_sums_f64(double* out2, const double* A, const double* B, int64_t count, void* ws, void* stream);
+
+/* ---- QR / SVD:  pyLOM/vmmath/src/svd.h:12-39 -------------------------------------------------- */
+/* Workspace for one tall matrix (m x n): padded factorisation buffer + T factors + scratch. */
+size_t pl_qr_workspace_bytes(int64_t m, int64_t n);
+
+/* First half of dqr (svd.c:280-321, LAPACKE_dgeqrf): copy A (optionally minus its row means, the
+ * POD.run centering) into the workspace, Householder-factor it there, return R (n x n, zeros below
+ * the diagonal, svd.c:304-307).  A is not modified.  X_mean (m) may be NULL when center == 0. */
+int pl_qr_factor_f64(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center,
+                     void* ws, size_t ws_bytes, void* stream);
+/* Second half of dqr (LAPACKE_dorgqr) fused with the back-multiplies of dtsqr/dtsqr_svd
+ * (dmatmul at svd.c:673 and svd.c:708):  U(m, nw) = Q1 * W, W (n x nw, ldw) on the device.
+ * W == NULL gives U = Q1 (nw must equal n).  Must follow pl_qr_factor_f64 on the same workspace.
+ * flags bit 0: Q1 has already been formed in this workspace by an earlier call. */
+int pl_qr_apply_q_f64(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n,
+                      int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces dsvd(double *U, double *S, double *VT, double *Y, m, n) for the square n x n case it is
+ * used for on this path (svd.c:83-139, call site svd.c:706).  S descending, VT = V^T. */
+size_t pl_svd_workspace_bytes(int64_t n);
+int pl_svd_f64(double* U, double* S, double* VT, const double* Y, int64_t n, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces dtsqr_svd(double *Ui, double *S, double *VT, double *Ai, m, n) on ONE rank  svd.c:678-712.
+ * ws: >= pl_qr_workspace_bytes(m, n).  With several ranks the host layer composes
+ * pl_qr_factor_f64 -> NCCL all-gather of R -> pl_qr_factor_f64/apply on the stack -> pl_svd_f64 ->
+ * pl_qr_apply_q_f64 (see pyloworder_b200/vmmath/svd.py). */
+int pl_tsqr_svd_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n,
+                    void* ws, size_t ws_bytes, void* stream);
+/* POD.run(remove_mean) on one rank: _drun in pyLOM/POD/wrapper.pyx:95-151 (centering fused into the
+ * copy that feeds the factorisation).  X_mean (m) receives the row means when remove_mean != 0. */
+int pl_pod_run_f64(double* U, double* S, double* VT, double* X_mean, const double* X, int64_t m, int64_t n,
+                   int remove_mean, void* ws, size_t ws_bytes, void* stream);
+/* POD.reconstruct: X(m,n) = U(m,N) diag(S) VT(N,n)   _dreconstruct, POD/wrapper.pyx:324-351 */
+int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S, const double* VT, int64_t ldvt,
+                       int64_t m, int64_t N, int64_t n, void* ws, size_t ws_bytes, void* stream);
+
+/* Same signature and meaning as the reference's dtsqr_svd but HOST pointers (what a ctypes / Cython
+ * binding of the reference would pass): allocates device memory, copies in, computes, copies back. */
+int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n);
+
+/* instrumentation: number of kernel launches issued by this library since load */
+int64_t pl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

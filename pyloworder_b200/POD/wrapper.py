@@ -1,0 +1,64 @@
+"""POD.run / truncate / reconstruct with the reference's signatures (pyLOM/POD/wrapper.py:16-103,
+compiled twin pyLOM/POD/wrapper.pyx:95-377)."""
+import torch
+
+from .. import _lib, _dev
+from ..utils.cr import cr, cr_start, cr_stop
+from ..vmmath.svd import _tsqr_svd_dev
+from ..vmmath.truncation import compute_truncation_residual
+
+
+@cr('POD.run')
+def run(X, remove_mean=True, divide_variance=False, randomized=False, r=1, q=3, seed=-1):
+    """POD of the (row-distributed) snapshot matrix X(m_i, n).
+
+    Returns U (m_i, n) spatial modes, S (n) singular values, V (n, n) = V^T temporal coefficients.
+    X is not modified.  The centering (temporal_mean + subtract_mean, POD/wrapper.py:33-41) is fused
+    into the copy that feeds the factorisation.  `divide_variance` and `randomized` are outside the
+    B200 hot path and raise NotImplementedError.
+    """
+    if divide_variance:
+        raise NotImplementedError("POD.run(divide_variance=True) is not part of the B200 hot path yet")
+    if randomized:
+        raise NotImplementedError("POD.run(randomized=True) is not part of the B200 hot path yet")
+    Xd, kind = _dev.to_device(X, "X")
+    cr_start('POD.SVD', 0)
+    U, S, V, _ = _tsqr_svd_dev(Xd, center=bool(remove_mean))
+    cr_stop('POD.SVD', 0)
+    return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(V, kind)
+
+
+@cr('POD.truncate')
+def truncate(U, S, V, r=1e-8):
+    """Keep N modes: r >= 1 -> N = int(r); 0 < r < 1 -> residual target; r < 0 -> cumulative energy
+    (POD/wrapper.py:55-82).  Returns views U[:, :N], S[:N], V[:N, :] like the reference's .py path."""
+    N = int(r) if r >= 1 else compute_truncation_residual(S, r)
+    return U[:, :N], S[:N], V[:N, :]
+
+
+@cr('POD.reconstruct')
+def reconstruct(U, S, V):
+    """X(m_i, n) = U(m_i, N) diag(S) V(N, n); the temporal mean is NOT re-added (POD/wrapper.py:86-103)."""
+    kind = "torch"
+    if not (isinstance(U, torch.Tensor) and U.is_cuda):
+        U, kind = _dev.to_device(U, "U")
+    Sd, _ = _dev.to_device(S, "S")
+    Vd = V if (isinstance(V, torch.Tensor) and V.is_cuda) else _dev.to_device(V, "V")[0]
+    if U.dtype != torch.float64 or Vd.dtype != torch.float64:
+        raise NotImplementedError("only float64 is implemented on the B200 path")
+    if U.stride(1) != 1 and U.shape[1] > 1:
+        U = U.contiguous()
+    if Vd.stride(1) != 1 and Vd.shape[1] > 1:
+        Vd = Vd.contiguous()
+    m, N = U.shape
+    N2, n = Vd.shape
+    if N != N2 or Sd.numel() != N:
+        raise ValueError("reconstruct: inconsistent shapes")
+    ldu = U.stride(0) if m > 1 else N
+    ldv = Vd.stride(0) if N > 1 else n
+    X = torch.empty((m, n), dtype=torch.float64, device=U.device)
+    L = _lib.lib()
+    _, wp, wb = _dev.workspace(L.pl_matmul_workspace_bytes(n, N), "matmul", U.device)
+    _lib.check(L.pl_reconstruct_f64(X.data_ptr(), U.data_ptr(), ldu, Sd.data_ptr(), Vd.data_ptr(), ldv, m, N, n, wp, wb,
+                                    _dev.stream()), "reconstruct")
+    return _dev.from_device(X, kind)

@@ -1,0 +1,221 @@
+// C ABI of libpylom_b200 (declared in include/pylom_b200.h) -- thin composition of the kernels.
+#include "pl_common.cuh"
+#include "caqr.h"
+#include "../../include/pylom_b200.h"
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+namespace pl {
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+const char* last_error() { return g_err; }
+void count_launches(long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+// ---- workspace layout for one tall matrix ---------------------------------------------------
+struct WsLayout {
+  Plan plan;
+  size_t vb, tws, vup, ptmp, r, bp, ur, svd, vt, s, total;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static WsLayout make_layout(int64_t m, int64_t n) {
+  WsLayout L;
+  L.plan = make_plan(m, n);
+  const Plan& P = L.plan;
+  size_t off = 0;
+  L.vb = off;   off += al((size_t)P.mrows * P.npad * 8);
+  L.tws = off;  off += al((size_t)P.t_tiles * NB * NB * 8);
+  L.vup = off;  off += al((size_t)(P.vup_tiles > 0 ? P.vup_tiles : 1) * TB * NB * 8);
+  L.ptmp = off; off += al((size_t)P.mrows * NB * 8);
+  L.r = off;    off += al((size_t)n * n * 8);
+  const int64_t kp = round_up(n, 16), np = round_up(n, 64);
+  L.bp = off;   off += al((size_t)kp * np * 8);
+  L.ur = off;   off += al((size_t)n * n * 8);
+  L.vt = off;   off += al((size_t)n * n * 8);
+  L.s = off;    off += al((size_t)n * 8);
+  L.svd = off;  off += al((size_t)svd_small_scratch_doubles(n) * 8);
+  L.total = off;
+  return L;
+}
+static inline double* at(void* ws, size_t off) { return reinterpret_cast<double*>(static_cast<char*>(ws) + off); }
+
+static int check_ws(const WsLayout& L, void* ws, size_t ws_bytes, int argpos) {
+  if (!ws || ws_bytes < L.total) { set_error("workspace too small: need %zu bytes, got %zu", L.total, ws_bytes); return -argpos; }
+  if (reinterpret_cast<uintptr_t>(ws) & 255) { set_error("workspace must be 256-byte aligned"); return -argpos; }
+  return 0;
+}
+
+static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center, void* ws,
+                     const WsLayout& L, cudaStream_t st) {
+  const Plan& P = L.plan;
+  double* Vb = at(ws, L.vb);
+  int rc;
+  if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
+  else rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
+  if (rc) return rc;
+  PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
+  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), st);
+  if (rc) return rc;
+  if (R) rc = caqr_extract_r(P, Vb, R, n, st);
+  return rc;
+}
+
+static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n, int flags,
+                      void* ws, const WsLayout& L, cudaStream_t st) {
+  const Plan& P = L.plan;
+  double* Vb = at(ws, L.vb);
+  int rc;
+  if (!(flags & 1)) {
+    rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.ptmp), st);
+    if (rc) return rc;
+  }
+  if (!W) {
+    if (nw != n) { set_error("apply_q: W == NULL needs nw == n"); return -5; }
+    return copy_pad(U, ldu, Vb, P.npad, m, n, n, st);
+  }
+  if (nw > n) { set_error("apply_q: nw > n"); return -5; }
+  const int64_t kp = round_up(n, 16), np = round_up(nw, 64);
+  double* Bp = at(ws, L.bp);
+  rc = pad_small(Bp, kp, np, W, ldw, n, nw, nullptr, st);
+  if (rc) return rc;
+  return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, n, st);
+}
+}  // namespace pl
+
+using namespace pl;
+
+#define PL_ARG(cond, pos, msg) do { if (!(cond)) { set_error("bad argument %d: %s", pos, msg); return -(pos); } } while (0)
+
+extern "C" {
+
+int pl_version(void) { return 100; }
+const char* pl_last_error(void) { return last_error(); }
+int64_t pl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pl_temporal_mean_f64(double* out, const double* X, int64_t m, int64_t n, void* stream) {
+  PL_ARG(m >= 0 && n > 0, 3, "m >= 0, n > 0");
+  return temporal_mean(out, X, m, n, (cudaStream_t)stream);
+}
+int pl_subtract_mean_f64(double* out, const double* X, const double* X_mean, int64_t m, int64_t n, void* stream) {
+  PL_ARG(m >= 0 && n > 0, 4, "m >= 0, n > 0");
+  return subtract_mean(out, n, X, X_mean, m, n, n, (cudaStream_t)stream);
+}
+int pl_center_f64(double* Y, double* X_mean, const double* X, int64_t m, int64_t n, void* stream) {
+  PL_ARG(m >= 0 && n > 0, 4, "m >= 0, n > 0");
+  return center_rows(Y, n, X_mean, X, m, n, n, (cudaStream_t)stream);
+}
+int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream) {
+  return vecmat(C, n, v, A, n, m, n, (cudaStream_t)stream);
+}
+
+size_t pl_matmul_workspace_bytes(int64_t n, int64_t k) { return (size_t)round_up(k, 16) * round_up(n, 64) * 8 + 256; }
+int pl_matmul_f64(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
+                  int64_t n, int64_t k, void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(m >= 0 && n > 0 && k > 0, 7, "sizes");
+  PL_ARG(ws && ws_bytes >= pl_matmul_workspace_bytes(n, k), 10, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t kp = round_up(k, 16), np = round_up(n, 64);
+  int rc = pad_small((double*)ws, kp, np, B, ldb, k, n, nullptr, st);
+  if (rc) return rc;
+  return gemm_tall(C, ldc, A, lda, (double*)ws, np, m, n, k, st);
+}
+
+size_t pl_rmse_workspace_bytes(void) { return SUMSQ_SCRATCH_DOUBLES * 8; }
+int pl_rmse_sums_f64(double* out2, const double* A, const double* B, int64_t count, void* ws, void* stream) {
+  return sumsq_diff(out2, (double*)ws, A, B, count, (cudaStream_t)stream);
+}
+
+size_t pl_qr_workspace_bytes(int64_t m, int64_t n) {
+  if (m <= 0 || n <= 0) return 0;
+  return make_layout(m, n).total;
+}
+
+int pl_qr_factor_f64(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center, void* ws,
+                     size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n, 4, "need m >= n > 0 (the reference has the same precondition, svd.py:69)");
+  PL_ARG(!center || X_mean, 2, "X_mean required when center != 0");
+  WsLayout L = make_layout(m, n);
+  int rc = check_ws(L, ws, ws_bytes, 7);
+  if (rc) return rc;
+  return qr_factor(R, X_mean, A, m, n, center, ws, L, (cudaStream_t)stream);
+}
+
+int pl_qr_apply_q_f64(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n, int flags,
+                      void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n, 6, "need m >= n > 0");
+  WsLayout L = make_layout(m, n);
+  int rc = check_ws(L, ws, ws_bytes, 9);
+  if (rc) return rc;
+  return qr_apply_q(U, ldu, W, ldw, nw, m, n, flags, ws, L, (cudaStream_t)stream);
+}
+
+size_t pl_svd_workspace_bytes(int64_t n) { return (size_t)svd_small_scratch_doubles(n) * 8 + 256; }
+int pl_svd_f64(double* U, double* S, double* VT, const double* Y, int64_t n, void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0, 5, "n > 0");
+  PL_ARG(ws && ws_bytes >= pl_svd_workspace_bytes(n), 6, "workspace too small");
+  return svd_small(U, n, S, VT, n, Y, n, n, (double*)ws, nullptr, (cudaStream_t)stream);
+}
+
+static int tsqr_svd_impl(double* Ui, double* S, double* VT, double* X_mean, const double* Ai, int64_t m, int64_t n,
+                         int center, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WsLayout L = make_layout(m, n);
+  int rc = check_ws(L, ws, ws_bytes, 9);
+  if (rc) return rc;
+  double* R = at(ws, L.r);
+  rc = qr_factor(R, X_mean, Ai, m, n, center, ws, L, st);
+  if (rc) return rc;
+  double* Ur = at(ws, L.ur);
+  rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
+  if (rc) return rc;
+  return qr_apply_q(Ui, n, Ur, n, n, m, n, 0, ws, L, st);
+}
+
+int pl_tsqr_svd_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n, void* ws, size_t ws_bytes,
+                    void* stream) {
+  PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
+  return tsqr_svd_impl(Ui, S, VT, nullptr, Ai, m, n, 0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pl_pod_run_f64(double* U, double* S, double* VT, double* X_mean, const double* X, int64_t m, int64_t n, int remove_mean,
+                   void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n, 6, "need m >= n > 0");
+  PL_ARG(!remove_mean || X_mean, 4, "X_mean required when remove_mean != 0");
+  return tsqr_svd_impl(U, S, VT, X_mean, X, m, n, remove_mean ? 1 : 0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S, const double* VT, int64_t ldvt, int64_t m,
+                       int64_t N, int64_t n, void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(m >= 0 && N > 0 && n > 0, 7, "sizes");
+  PL_ARG(ws && ws_bytes >= pl_matmul_workspace_bytes(n, N), 10, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t kp = round_up(N, 16), np = round_up(n, 64);
+  int rc = pad_small((double*)ws, kp, np, VT, ldvt, N, n, S, st);   // diag(S) V folded into the packing
+  if (rc) return rc;
+  return gemm_tall(X, n, U, ldu, (double*)ws, np, m, n, N, st);
+}
+
+int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
+  PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
+  const size_t ab = (size_t)m * n * 8, wsb = pl_qr_workspace_bytes(m, n);
+  double *dA = nullptr, *dU = nullptr, *dS = nullptr, *dV = nullptr; void* ws = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() { cudaFree(dA); cudaFree(dU); cudaFree(dS); cudaFree(dV); cudaFree(ws); };
+#define PL_H(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); cleanup(); return 1000 + (int)_e; } } while (0)
+  PL_H(cudaMalloc(&dA, ab)); PL_H(cudaMalloc(&dU, ab));
+  PL_H(cudaMalloc(&dS, (size_t)n * 8)); PL_H(cudaMalloc(&dV, (size_t)n * n * 8)); PL_H(cudaMalloc(&ws, wsb));
+  PL_H(cudaMemcpyAsync(dA, Ai, ab, cudaMemcpyHostToDevice, st));
+  rc = pl_tsqr_svd_f64(dU, dS, dV, dA, m, n, ws, wsb, st);
+  if (rc) { cleanup(); return rc; }
+  PL_H(cudaMemcpyAsync(Ui, dU, ab, cudaMemcpyDeviceToHost, st));
+  PL_H(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  PL_H(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
+  PL_H(cudaStreamSynchronize(st));
+  cleanup();
+  return 0;
+}
+
+}  // extern "C"

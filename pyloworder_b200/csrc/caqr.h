@@ -1,0 +1,49 @@
+// Internal C++ interface between the translation units of libpylom_b200.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+namespace pl {
+
+struct Level {
+  int64_t nblk;     // NB-row blocks at this level
+  int64_t bs;       // row distance between consecutive blocks
+  int64_t ntiles;   // tiles of G blocks
+  int s;            // tiles per strip (flat tree inside a CTA)
+  int64_t nstrips;
+  int64_t t_off;    // tile offset of this level in the T store
+  int64_t v_off;    // tile offset in the upper-level reflector store (-1 at level 0: in place)
+};
+
+struct Plan {
+  int64_t m, n, npad, mrows;
+  int K;                                   // panels
+  std::vector<std::vector<Level>> panels;  // [panel][level]
+  int64_t t_tiles, vup_tiles;              // totals
+};
+
+Plan make_plan(int64_t m, int64_t n);
+int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_t st);
+int caqr_extract_r(const Plan& P, const double* Vb, double* R, int64_t ldr, cudaStream_t st);
+int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, double* Ptmp, cudaStream_t st);
+
+// center.cu
+int temporal_mean(double* out, const double* X, int64_t m, int64_t n, cudaStream_t st);
+int subtract_mean(double* out, int64_t ldo, const double* X, const double* mean, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st);
+int center_rows(double* Y, int64_t ldy, double* mean, const double* X, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st);
+int copy_pad(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st);
+int vecmat(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n, cudaStream_t st);
+int sumsq_diff(double* out2, double* scratch, const double* A, const double* B, int64_t cnt, cudaStream_t st);
+constexpr int SUMSQ_SCRATCH_DOUBLES = 2 * 148 * 4;
+
+// gemm.cu :  C[m x n] (ldc) = A[m x k] (lda) * Bp[kp x np] (ldb = np), Bp zero padded to kp%16==0, np%64==0
+int gemm_tall(double* C, int64_t ldc, const double* A, int64_t lda, const double* Bp, int64_t ldb, int64_t m, int64_t n, int64_t k, cudaStream_t st);
+int pad_small(double* dst, int64_t rows_p, int64_t cols_p, const double* src, int64_t lds, int64_t rows, int64_t cols, const double* rowscale, cudaStream_t st);
+
+// svd_small.cu : R (n x n, ldr) = Ur diag(S) VT ; Ur, VT n x n with given ld; scratch >= 2*n*n + 4*n + 64 doubles
+int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, const double* R, int64_t ldr, int64_t n,
+              double* scratch, int* sweeps_out, cudaStream_t st);
+int64_t svd_small_scratch_doubles(int64_t n);
+
+}  // namespace pl

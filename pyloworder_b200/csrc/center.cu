@@ -1,0 +1,174 @@
+// Streaming row kernels: temporal_mean / subtract_mean / fused centering (+ optional padding into
+// the factorisation buffer), vecmat, RMSE partial sums.  All HBM-bound: one read (+ one write) of
+// the snapshot matrix, 8/16-byte coalesced accesses, a group of lanes per row, shuffle reductions.
+//
+// Reference semantics: pyLOM/vmmath/src/averaging.c:29-46 (dtemporal_mean: row mean over the n
+// snapshots), :109-124 (dsubtract_mean), pyLOM/vmmath/src/vector_matrix.c:401-414 (dvecmat),
+// pyLOM/vmmath/src/stats.c:44-72 (dRMSE_relative sums).
+#include "pl_common.cuh"
+
+namespace pl {
+
+enum RowMode { ROW_MEAN = 0, ROW_SUB = 1, ROW_CENTER = 2, ROW_COPY = 3 };
+
+// One group of GS lanes per row (GS = 32 for n >= 32, smaller powers of two for short rows).
+// The row is read twice in ROW_CENTER; the second read hits L1/L2 (a row is <= 8 KiB).
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256) row_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src,
+                                                  int64_t lds, double* __restrict__ mean_out,
+                                                  const double* __restrict__ mean_in, int64_t m, int n, int gs,
+                                                  int pad_to) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % gs;                 // lane inside the row group
+  const int grp = lane / gs;                 // row group inside the warp
+  const int gpw = 32 / gs;                   // row groups per warp
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const double inv_n = 1.0 / (double)n;
+  for (int64_t row0 = warp * gpw; row0 < m; row0 += nwarps * gpw) {
+    const int64_t row = row0 + grp;
+    const bool live = row < m;
+    const double* x = src + (live ? row : 0) * lds;
+    double mu = 0.0;
+    if (MODE == ROW_MEAN || MODE == ROW_CENTER) {
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      if (live) {
+        if (VEC) {
+          const double2* xv = reinterpret_cast<const double2*>(x);
+          const int nv = n >> 1;
+          int j = sub;
+          for (; j + 3 * gs < nv; j += 4 * gs) {
+            double2 a = xv[j], b = xv[j + gs], c = xv[j + 2 * gs], d = xv[j + 3 * gs];
+            s0 += a.x + a.y; s1 += b.x + b.y; s2 += c.x + c.y; s3 += d.x + d.y;
+          }
+          for (; j < nv; j += gs) { double2 a = xv[j]; s0 += a.x + a.y; }
+        } else {
+          int j = sub;
+          for (; j + 3 * gs < n; j += 4 * gs) {
+            s0 += x[j]; s1 += x[j + gs]; s2 += x[j + 2 * gs]; s3 += x[j + 3 * gs];
+          }
+          for (; j < n; j += gs) s0 += x[j];
+        }
+      }
+      double s = (s0 + s1) + (s2 + s3);
+      for (int o = gs >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mu = s * inv_n;
+      if (live && sub == 0 && mean_out) mean_out[row] = mu;
+    } else if (MODE == ROW_SUB) {
+      if (live) mu = mean_in[row];
+    }
+    if (MODE != ROW_MEAN && live) {
+      double* y = dst + row * ldd;
+      if (VEC) {
+        const double2* xv = reinterpret_cast<const double2*>(x);
+        double2* yv = reinterpret_cast<double2*>(y);
+        const int nv = n >> 1;
+        for (int j = sub; j < nv; j += gs) {
+          double2 a = xv[j];
+          a.x -= mu; a.y -= mu;
+          yv[j] = a;
+        }
+        for (int j = nv + sub; j < (pad_to >> 1); j += gs) yv[j] = make_double2(0.0, 0.0);
+      } else {
+        for (int j = sub; j < n; j += gs) y[j] = x[j] - mu;
+        for (int j = n + sub; j < pad_to; j += gs) y[j] = 0.0;
+      }
+    }
+  }
+}
+
+static int pick_gs(int64_t n, bool vec) {
+  int64_t e = vec ? (n >> 1) : n;
+  int gs = 1;
+  while (gs < 32 && gs < e) gs <<= 1;
+  return gs;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE>
+static int launch_row(double* dst, int64_t ldd, const double* src, int64_t lds, double* mean_out,
+                      const double* mean_in, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return 0;
+  bool vec = (n % 2 == 0) && (lds % 2 == 0) && aligned16(src) &&
+             (MODE == ROW_MEAN || ((ldd % 2 == 0) && aligned16(dst) && (pad_to % 2 == 0)));
+  int gs = pick_gs(n, vec);
+  int64_t rows_per_block = 8 * (32 / gs);
+  int64_t blocks = ceil_div(m, rows_per_block);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (vec)
+    row_kernel<MODE, true><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, m, (int)n, gs, (int)pad_to);
+  else
+    row_kernel<MODE, false><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, m, (int)n, gs, (int)pad_to);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
+int temporal_mean(double* out, const double* X, int64_t m, int64_t n, cudaStream_t st) {
+  return launch_row<ROW_MEAN>(nullptr, 0, X, n, out, nullptr, m, n, n, st);
+}
+int subtract_mean(double* out, int64_t ldo, const double* X, const double* mean, int64_t m, int64_t n, int64_t pad_to,
+                  cudaStream_t st) {
+  return launch_row<ROW_SUB>(out, ldo, X, n, nullptr, mean, m, n, pad_to, st);
+}
+int center_rows(double* Y, int64_t ldy, double* mean, const double* X, int64_t m, int64_t n, int64_t pad_to,
+                cudaStream_t st) {
+  return launch_row<ROW_CENTER>(Y, ldy, X, n, mean, nullptr, m, n, pad_to, st);
+}
+int copy_pad(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m, int64_t n, int64_t pad_to,
+             cudaStream_t st) {
+  return launch_row<ROW_COPY>(dst, ldd, src, lds, nullptr, nullptr, m, n, pad_to, st);
+}
+
+// ---- vecmat: C[i,:] = v[i] * A[i,:] --------------------------------------------------------
+__global__ void vecmat_kernel(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = m * n;
+  for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = idx / n, j = idx - i * n;
+    C[i * ldc + j] = v[i] * A[i * lda + j];
+  }
+}
+int vecmat(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n, cudaStream_t st) {
+  if (m * n == 0) return 0;
+  int64_t blocks = ceil_div(m * n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  vecmat_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, ldc, v, A, lda, m, n);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- RMSE sums: out[0] = sum (A-B)^2, out[1] = sum A^2 (deterministic two-stage reduction) ----
+constexpr int RM_BLOCKS = 148 * 4;
+__global__ void __launch_bounds__(256) sumsq_partial(double* part, const double* A, const double* B, int64_t cnt) {
+  double s1 = 0, s2 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+    double a = A[i], d = a - B[i];
+    s1 += d * d; s2 += a * a;
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  __shared__ double sh[2][8];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < 8; i++) { a += sh[0][i]; b += sh[1][i]; }
+    part[blockIdx.x] = a; part[RM_BLOCKS + blockIdx.x] = b;
+  }
+}
+__global__ void sumsq_final(double* out, const double* part) {
+  double s1 = 0, s2 = 0;
+  for (int i = threadIdx.x; i < RM_BLOCKS; i += 32) { s1 += part[i]; s2 += part[RM_BLOCKS + i]; }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (threadIdx.x == 0) { out[0] = s1; out[1] = s2; }
+}
+int sumsq_diff(double* out2, double* scratch, const double* A, const double* B, int64_t cnt, cudaStream_t st) {
+  sumsq_partial<<<RM_BLOCKS, 256, 0, st>>>(scratch, A, B, cnt);
+  PL_LAUNCH_CHECK();
+  sumsq_final<<<1, 32, 0, st>>>(out2, scratch);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pl

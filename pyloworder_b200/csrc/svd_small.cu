@@ -1,0 +1,135 @@
+// SVD of the small n x n triangular factor on one GPU: one-sided Jacobi on the ROWS of R.
+//
+// Replaces `dsvd` = LAPACKE_dgesvd / dgesdd on R (pyLOM/vmmath/src/svd.c:83-139, called at
+// svd.c:706).  Left rotations G <- Rot * G make the rows of G = J R mutually orthogonal, so
+// G = diag(S) VT and R = J^T diag(S) VT, i.e. Ur = J^T.  Rows are contiguous in memory, the
+// rotations of one round-robin round are independent (n/2 CTAs), and Jacobi delivers singular
+// values to high *relative* accuracy, which the 1e-10 parity target on small sigma needs.
+// Orthogonalising the rows of R is the Drmac-Veselic "apply Jacobi to R^T" preconditioned variant.
+// Output ordering: S descending, VT rows = right singular vectors (the `V` every reference
+// routine returns, POD/wrapper.py:80).
+#include "pl_common.cuh"
+#include "caqr.h"
+#include <cmath>
+
+namespace pl {
+
+__global__ void jacobi_init_kernel(double* Gm, double* J, const double* R, int64_t ldr, int n) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  int r = (int)(idx / n), c = (int)(idx % n);
+  Gm[idx] = R[(int64_t)r * ldr + c];
+  J[idx] = (r == c) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double (*sh)[4]) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a; sh[1][w] = b; sh[2][w] = c; }
+  __syncthreads();
+  a = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+  b = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+  c = sh[2][0] + sh[2][1] + sh[2][2] + sh[2][3];
+}
+
+// One round of the round-robin ordering: CTA i rotates row pair (p, q).
+__global__ void __launch_bounds__(128) jacobi_round_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
+                                                           int round, double tol, int* __restrict__ rotations) {
+  __shared__ double sh[3][4];
+  const int i = blockIdx.x;
+  int p, q;
+  if (i == 0) { p = ne - 1; q = round; }
+  else { p = (round + i) % (ne - 1); q = (round - i + (ne - 1)) % (ne - 1); }
+  if (p >= n || q >= n) return;
+  if (p > q) { int tmp = p; p = q; q = tmp; }
+  double* gp = Gm + (int64_t)p * n; double* gq = Gm + (int64_t)q * n;
+  double a = 0, b = 0, c = 0;
+  for (int j = threadIdx.x; j < n; j += 128) { double x = gp[j], y = gq[j]; a += x * x; b += y * y; c += x * y; }
+  block_sum3(a, b, c, sh);
+  if (c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b)) return;
+  if (threadIdx.x == 0) atomicAdd(rotations, 1);
+  const double zeta = (b - a) / (2.0 * c);
+  const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+  double* jp = J + (int64_t)p * n; double* jq = J + (int64_t)q * n;
+  for (int j = threadIdx.x; j < n; j += 128) {
+    double x = gp[j], y = gq[j];
+    gp[j] = cs * x - sn * y; gq[j] = sn * x + cs * y;
+    double u = jp[j], v = jq[j];
+    jp[j] = cs * u - sn * v; jq[j] = sn * u + cs * v;
+  }
+}
+
+__global__ void __launch_bounds__(128) row_norm_kernel(double* s, const double* Gm, int n) {
+  __shared__ double sh[3][4];
+  const double* g = Gm + (int64_t)blockIdx.x * n;
+  // scaled two-pass norm is unnecessary here: rows are O(sigma), far from over/underflow for POD data
+  double a = 0, b = 0, c = 0;
+  for (int j = threadIdx.x; j < n; j += 128) { double x = g[j]; a += x * x; }
+  block_sum3(a, b, c, sh);
+  if (threadIdx.x == 0) s[blockIdx.x] = sqrt(a);
+}
+
+__global__ void rank_kernel(int* rank, const double* s, int n) {
+  for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < n; k += blockDim.x * gridDim.x) {
+    const double sk = s[k];
+    int r = 0;
+    for (int j = 0; j < n; j++) { double sj = s[j]; r += (sj > sk) || (sj == sk && j < k); }
+    rank[k] = r;
+  }
+}
+
+__global__ void __launch_bounds__(128) svd_scatter_kernel(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt,
+                                                          const double* Gm, const double* J, const double* s,
+                                                          const int* rank, int n) {
+  const int k = blockIdx.x, r = rank[k];
+  const double sk = s[k], inv = sk > 0.0 ? 1.0 / sk : 0.0;
+  if (threadIdx.x == 0) S[r] = sk;
+  for (int j = threadIdx.x; j < n; j += 128) {
+    VT[(int64_t)r * ldvt + j] = Gm[(int64_t)k * n + j] * inv;
+    Ur[(int64_t)j * ldu + r] = J[(int64_t)k * n + j];
+  }
+}
+
+int64_t svd_small_scratch_doubles(int64_t n) { return 2 * n * n + 2 * n + 64; }
+
+int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, const double* R, int64_t ldr, int64_t n,
+              double* scratch, int* sweeps_out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  double* Gm = scratch;
+  double* J = Gm + n * n;
+  double* s = J + n * n;
+  int* rank = reinterpret_cast<int*>(s + n);
+  int* rot = rank + n;     // inside the 64-double tail
+  const int ni = (int)n, ne = ni + (ni & 1);
+  jacobi_init_kernel<<<(unsigned)ceil_div(n * n, 256), 256, 0, st>>>(Gm, J, R, ldr, ni);
+  PL_LAUNCH_CHECK();
+  const double tol = 2.0 * std::sqrt((double)n) * 2.220446049250313e-16;
+  int sweeps = 0;
+  if (ni > 1) {
+    const int max_sweeps = 60;
+    for (; sweeps < max_sweeps;) {
+      PL_CUDA(cudaMemsetAsync(rot, 0, sizeof(int), st));
+      for (int r = 0; r < ne - 1; r++) {
+        jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot);
+      }
+      PL_LAUNCH_CHECK();
+      count_launches(ne - 2);
+      int h = 0;
+      PL_CUDA(cudaMemcpyAsync(&h, rot, sizeof(int), cudaMemcpyDeviceToHost, st));
+      PL_CUDA(cudaStreamSynchronize(st));
+      sweeps++;
+      if (h == 0) break;
+    }
+    if (sweeps >= max_sweeps) { set_error("svd_small: Jacobi did not converge in %d sweeps", max_sweeps); return 2; }
+  }
+  row_norm_kernel<<<ni, 128, 0, st>>>(s, Gm, ni);
+  rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(rank, s, ni);
+  svd_scatter_kernel<<<ni, 128, 0, st>>>(Ur, ldu, S, VT, ldvt, Gm, J, s, rank, ni);
+  PL_LAUNCH_CHECK();
+  count_launches(2);
+  if (sweeps_out) *sweeps_out = sweeps;
+  return 0;
+}
+
+}  // namespace pl

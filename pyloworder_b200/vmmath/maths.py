@@ -1,0 +1,72 @@
+"""matmul / vecmat / matmulp (pyLOM/vmmath/maths.py:76-129, src/vector_matrix.c:206-242,344-356,401-414)."""
+import torch
+
+from .. import _lib, _dev
+from ..utils.cr import cr
+from ..utils.parall import mpi_reduce
+
+
+def _strided2d(t):
+    """Accept row-major tensors whose rows are contiguous (views from POD.truncate)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D array")
+    if t.stride(1) != 1 and t.shape[1] > 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    if ld < t.shape[1]:
+        t = t.contiguous(); ld = t.shape[1]
+    return t, ld
+
+
+def _to_dev_keep_view(x, what):
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64:
+        return x, "torch"
+    return _dev.to_device(x, what)
+
+
+@cr('math.matmul')
+def matmul(A, B):
+    """C(M,N) = A(M,Q) x B(Q,N) on the FP64 tensor cores."""
+    Ad, kind = _to_dev_keep_view(A, "A")
+    Bd, _ = _to_dev_keep_view(B, "B")
+    Ad, lda = _strided2d(Ad)
+    Bd, ldb = _strided2d(Bd)
+    m, k = Ad.shape
+    k2, n = Bd.shape
+    if k != k2:
+        raise ValueError(f"matmul: inner dimensions differ ({k} vs {k2})")
+    C = torch.empty((m, n), dtype=torch.float64, device=Ad.device)
+    L = _lib.lib()
+    _, wp, wb = _dev.workspace(L.pl_matmul_workspace_bytes(n, k), "matmul", Ad.device)
+    _lib.check(L.pl_matmul_f64(C.data_ptr(), n, Ad.data_ptr(), lda, Bd.data_ptr(), ldb, m, n, k, wp, wb, _dev.stream()),
+               "matmul")
+    return _dev.from_device(C, kind)
+
+
+@cr('math.matmulp')
+def matmulp(A, B):
+    """C = A x B with the result summed over ranks (rows of B / columns of A are distributed)."""
+    Ad, kind = _to_dev_keep_view(A, "A")
+    C = matmul(Ad, _to_dev_keep_view(B, "B")[0])
+    return _dev.from_device(mpi_reduce(C, op='sum', all=True), kind)
+
+
+@cr('math.vecmat')
+def vecmat(v, A):
+    """C[i,:] = v[i] * A[i,:]."""
+    vd, _ = _dev.to_device(v, "v")
+    Ad, kind = _dev.to_device(A, "A")
+    m, n = Ad.shape
+    C = torch.empty_like(Ad)
+    _lib.check(_lib.lib().pl_vecmat_f64(C.data_ptr(), vd.data_ptr(), Ad.data_ptr(), m, n, _dev.stream()), "vecmat")
+    return _dev.from_device(C, kind)
+
+
+def vector_sum(v, start=0):
+    """Sum of v[start:] (pyLOM/vmmath/maths.py:32-44) -- O(n) scalar work on the n singular values."""
+    return float(torch.as_tensor(v)[start:].sum())
+
+
+def vector_norm(v, start=0):
+    """2-norm of v[start:] (pyLOM/vmmath/maths.py:47-59)."""
+    return float(torch.linalg.vector_norm(torch.as_tensor(v)[start:]))

@@ -1,0 +1,158 @@
+"""qr / svd / tsqr / tsqr_svd -- pyLOM/vmmath/svd.py:28-118,227-252 (src/svd.c:83-139,280-321,565-712).
+
+Single rank: one C call (`pl_tsqr_svd_f64`).  P ranks (one process per GPU, torch.distributed):
+
+    R_i        = local Householder QR (CUDA)                      <- dqr at svd.c:594
+    Rstack     = ONE all-gather of the n x n R_i (NCCL/NVLink)    <- replaces the butterfly svd.c:602-669
+    R, Q2      = Householder QR of the (P n) x n stack, redundantly on every GPU (bit-identical)
+    Ur, S, VT  = Jacobi SVD of R (CUDA)                           <- dsvd at svd.c:706
+    U_i        = Q1_i (Q2_i Ur)                                   <- dmatmul at svd.c:673 and :708 fused
+
+TSQR is valid for any reduction tree (Demmel et al. 2012, the paper svd.py:58 cites), so the flat
+all-gather tree gives the same R up to row signs.  S and VT are identical on all ranks.
+"""
+import torch
+
+from .. import _lib, _dev
+from ..utils.cr import cr, cr_start, cr_stop
+from ..utils import parall
+
+
+def next_power_of_2(n):
+    """pyLOM/vmmath/svd.py:17-25."""
+    p = 1
+    if n and not (n & (n - 1)):
+        return n
+    while p < n:
+        p <<= 1
+    return p
+
+
+class CudaEngine:
+    """The device operations the multi-rank composition needs; tests inject a CPU stand-in."""
+
+    def factor(self, A, tag, center=False):
+        m, n = A.shape
+        L = _lib.lib()
+        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, A.device)
+        R = torch.empty((n, n), dtype=torch.float64, device=A.device)
+        mean = torch.empty(m, dtype=torch.float64, device=A.device) if center else None
+        _lib.check(L.pl_qr_factor_f64(R.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n, int(center), wp, wb, _dev.stream()),
+                   "qr_factor")
+        return R, mean
+
+    def apply_q(self, shape, W, tag, device):
+        """U = Q1 W for the matrix last factored under `tag` (W None -> explicit Q1)."""
+        m, n = shape
+        L = _lib.lib()
+        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, device)
+        nw = n if W is None else W.shape[1]
+        U = torch.empty((m, nw), dtype=torch.float64, device=device)
+        ldw = 0 if W is None else W.stride(0)
+        _lib.check(L.pl_qr_apply_q_f64(U.data_ptr(), nw, _dev.ptr(W), ldw, nw, m, n, 0, wp, wb, _dev.stream()), "qr_apply_q")
+        return U
+
+    def svd(self, R):
+        n = R.shape[0]
+        L = _lib.lib()
+        _, wp, wb = _dev.workspace(L.pl_svd_workspace_bytes(n), "svd", R.device)
+        U = torch.empty((n, n), dtype=torch.float64, device=R.device)
+        S = torch.empty(n, dtype=torch.float64, device=R.device)
+        VT = torch.empty((n, n), dtype=torch.float64, device=R.device)
+        _lib.check(L.pl_svd_f64(U.data_ptr(), S.data_ptr(), VT.data_ptr(), R.data_ptr(), n, wp, wb, _dev.stream()), "svd")
+        return U, S, VT
+
+    def tsqr_svd_single(self, A, center=False):
+        m, n = A.shape
+        L = _lib.lib()
+        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), "local", A.device)
+        U = torch.empty((m, n), dtype=torch.float64, device=A.device)
+        S = torch.empty(n, dtype=torch.float64, device=A.device)
+        VT = torch.empty((n, n), dtype=torch.float64, device=A.device)
+        mean = torch.empty(m, dtype=torch.float64, device=A.device) if center else None
+        _lib.check(L.pl_pod_run_f64(U.data_ptr(), S.data_ptr(), VT.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n,
+                                    int(center), wp, wb, _dev.stream()), "tsqr_svd")
+        return U, S, VT, mean
+
+    def allgather_rows(self, R):
+        return parall.mpi_allgather_rows(R)
+
+
+_engine = CudaEngine()
+
+
+def _check_shape(A):
+    if A.dim() != 2:
+        raise ValueError("expected a 2-D array (m, n)")
+    m, n = A.shape
+    if m < n:
+        raise ValueError(f"every rank needs at least n rows (got m_i={m} < n={n}); "
+                         "the reference has the same precondition (pyLOM/vmmath/svd.py:69)")
+
+
+def _tsqr_svd_dev(Ad, center=False, engine=None):
+    """Core composition on device tensors.  Returns (U_i, S, VT, mean_i)."""
+    eng = engine or _engine
+    _check_shape(Ad)
+    P, rank = parall.size(), parall.rank()
+    if P == 1:
+        return eng.tsqr_svd_single(Ad, center)
+    m, n = Ad.shape
+    R_i, mean = eng.factor(Ad, "local", center)
+    cr_start('math.tsqr.allgather')
+    Rstack = eng.allgather_rows(R_i)
+    cr_stop('math.tsqr.allgather')
+    R, _ = eng.factor(Rstack, "stack", False)
+    Ur, S, VT = eng.svd(R)
+    Wfull = eng.apply_q((P * n, n), Ur, "stack", Ad.device)        # Q2 Ur, (P n) x n, tiny
+    U = eng.apply_q((m, n), Wfull[rank * n:(rank + 1) * n], "local", Ad.device)
+    return U, S, VT, mean
+
+
+@cr('math.tsqr_svd')
+def tsqr_svd(Ai):
+    """SVD of the row-distributed matrix via TSQR.  Ai(m_i,n) -> Ui(m_i,n), S(n), V(n,n) = V^T."""
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    U, S, VT, _ = _tsqr_svd_dev(Ad)
+    return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)
+
+
+@cr('math.tsqr')
+def tsqr(Ai):
+    """Parallel QR: Qi(m_i,n), R(n,n) identical on all ranks (pyLOM/vmmath/svd.py:49-118)."""
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    _check_shape(Ad)
+    eng = _engine
+    P, rank = parall.size(), parall.rank()
+    m, n = Ad.shape
+    R_i, _ = eng.factor(Ad, "local")
+    if P == 1:
+        Q = eng.apply_q((m, n), None, "local", Ad.device)
+        return _dev.from_device(Q, kind), _dev.from_device(R_i, kind)
+    Rstack = eng.allgather_rows(R_i)
+    R, _ = eng.factor(Rstack, "stack")
+    Q2 = eng.apply_q((P * n, n), None, "stack", Ad.device)
+    Q = eng.apply_q((m, n), Q2[rank * n:(rank + 1) * n], "local", Ad.device)
+    return _dev.from_device(Q, kind), _dev.from_device(R, kind)
+
+
+@cr('math.qr')
+def qr(A):
+    """Thin Householder QR of a local matrix: Q(m,n), R(n,n) (pyLOM/vmmath/svd.py:28-36)."""
+    Ad, kind = _dev.to_device(A, "A")
+    _check_shape(Ad)
+    m, n = Ad.shape
+    R, _ = _engine.factor(Ad, "local")
+    Q = _engine.apply_q((m, n), None, "local", Ad.device)
+    return _dev.from_device(Q, kind), _dev.from_device(R, kind)
+
+
+@cr('math.svd')
+def svd(A, method='gesdd'):
+    """Thin SVD of a small square matrix (the n x n R of this path): U, S (descending), V^T
+    (pyLOM/vmmath/svd.py:38-47).  `method` is accepted for signature compatibility."""
+    Ad, kind = _dev.to_device(A, "A")
+    if Ad.dim() != 2 or Ad.shape[0] != Ad.shape[1]:
+        raise NotImplementedError("svd: only the square n x n case of the TSQR path is implemented; use tsqr_svd for tall matrices")
+    U, S, VT = _engine.svd(Ad)
+    return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)

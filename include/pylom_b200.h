@@ -88,6 +88,10 @@ int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, in
 
 /* instrumentation: number of kernel launches issued by this library since load */
 int64_t pl_launch_count(void);
+/* optional CUDA-event timing per kernel class (0 copy/center, 1 panel, 2 update(factor), 3 update(form Q),
+ * 4 tall GEMM, 5 small SVD, 6 misc); pl_profile_read synchronises, fills ms / launch counts and resets. */
+void pl_profile_enable(int on);
+int pl_profile_read(double* ms_by_class, int64_t* launches_by_class, int ncls);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace pl {
 static thread_local char g_err[512] = "";
@@ -14,6 +15,16 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 void count_launches(long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+// ---- profiling ------------------------------------------------------------------------------
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(int cls, cudaStream_t st) {
+  ProfRec r; r.cls = cls; cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); cudaEventRecord(r.e0, st); g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 
 // ---- workspace layout for one tall matrix ---------------------------------------------------
 struct WsLayout {
@@ -53,10 +64,13 @@ static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int6
   const Plan& P = L.plan;
   double* Vb = at(ws, L.vb);
   int rc;
-  if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
-  else rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
-  if (rc) return rc;
-  PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
+  {
+    ProfScope ps(PROF_COPY, st);
+    if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
+    else rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
+    if (rc) return rc;
+    PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
+  }
   rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), st);
   if (rc) return rc;
   if (R) rc = caqr_extract_r(P, Vb, R, n, st);
@@ -81,6 +95,7 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   double* Bp = at(ws, L.bp);
   rc = pad_small(Bp, kp, np, W, ldw, n, nw, nullptr, st);
   if (rc) return rc;
+  ProfScope ps(PROF_GEMM, st);
   return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, n, st);
 }
 }  // namespace pl
@@ -94,6 +109,18 @@ extern "C" {
 int pl_version(void) { return 100; }
 const char* pl_last_error(void) { return last_error(); }
 int64_t pl_launch_count(void) { return (int64_t)g_launches.load(); }
+void pl_profile_enable(int on) { g_prof_on = on != 0; }
+int pl_profile_read(double* ms_by_class, int64_t* launches_by_class, int ncls) {
+  for (int i = 0; i < ncls; i++) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.cls < ncls) { ms_by_class[r.cls] += ms; launches_by_class[r.cls] += 1; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int pl_temporal_mean_f64(double* out, const double* X, int64_t m, int64_t n, void* stream) {
   PL_ARG(m >= 0 && n > 0, 3, "m >= 0, n > 0");
@@ -168,7 +195,10 @@ static int tsqr_svd_impl(double* Ui, double* S, double* VT, double* X_mean, cons
   rc = qr_factor(R, X_mean, Ai, m, n, center, ws, L, st);
   if (rc) return rc;
   double* Ur = at(ws, L.ur);
-  rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
+  {
+    ProfScope ps(PROF_SVD, st);
+    rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
+  }
   if (rc) return rc;
   return qr_apply_q(Ui, n, Ur, n, n, m, n, 0, ws, L, st);
 }

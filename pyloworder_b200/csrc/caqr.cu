@@ -478,7 +478,10 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
     B.Tl = A.Tl + done * L.s * (NB * NB);
     if (B.Vupl) B.Vupl = A.Vupl + done * L.s * (TB * NB);
     dim3 grid((unsigned)(nchunk0 + nchunk1), (unsigned)ny);
-    caqr_update_kernel<<<grid, 256, sizeof(UpdSmem), st>>>(B);
+    {
+      ProfScope ps(forward ? PROF_UPDATE_F : PROF_UPDATE_Q, st);
+      caqr_update_kernel<<<grid, 256, sizeof(UpdSmem), st>>>(B);
+    }
     PL_LAUNCH_CHECK();
     done += ny;
   }
@@ -491,9 +494,12 @@ int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
     for (size_t li = 0; li < P.panels[p].size(); li++) {
       const Level& L = P.panels[p][li];
-      caqr_panel_kernel<<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
-                                                             li > 0, Tws + L.t_off * (NB * NB),
-                                                             li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+      {
+        ProfScope ps(PROF_PANEL, st);
+        caqr_panel_kernel<<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
+                                                               li > 0, Tws + L.t_off * (NB * NB),
+                                                               li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+      }
       PL_LAUNCH_CHECK();
       int rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
       if (rc) return rc;
@@ -519,14 +525,20 @@ int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup,
   for (int p = P.K - 1; p >= 0; p--) {
     const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
-    ptmp_init_kernel<<<148 * 8, 256, 0, st>>>(Ptmp, row0, P.mrows);
+    {
+      ProfScope ps(PROF_MISC, st);
+      ptmp_init_kernel<<<148 * 8, 256, 0, st>>>(Ptmp, row0, P.mrows);
+    }
     PL_LAUNCH_CHECK();
     for (int li = (int)P.panels[p].size() - 1; li >= 0; li--) {
       const Level& L = P.panels[p][li];
       int rc = launch_update(P, p, L, li, Vb, Tws, Vup, Ptmp, NB, 0, 1, Vb, P.npad, col0 + NB, ntrail, 0, st);
       if (rc) return rc;
     }
-    ptmp_copyback_kernel<<<148 * 8, 256, 0, st>>>(Vb, P.npad, col0, Ptmp, row0, P.mrows);
+    {
+      ProfScope ps(PROF_MISC, st);
+      ptmp_copyback_kernel<<<148 * 8, 256, 0, st>>>(Vb, P.npad, col0, Ptmp, row0, P.mrows);
+    }
     PL_LAUNCH_CHECK();
   }
   return 0;

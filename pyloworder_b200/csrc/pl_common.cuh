@@ -36,6 +36,17 @@ void count_launches(long long k);   // instrumentation: kernels launched by this
     }                                                                                      \
   } while (0)
 
+// ---- optional per-kernel-class event timing (bench.py roofline leg; off by default) ---------
+enum ProfClass { PROF_COPY = 0, PROF_PANEL = 1, PROF_UPDATE_F = 2, PROF_UPDATE_Q = 3, PROF_GEMM = 4, PROF_SVD = 5, PROF_MISC = 6, PROF_NCLS = 7 };
+bool prof_enabled();
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(int cls, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_begin(cls, st); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -1,0 +1,234 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the C ABI,
+against the CPU oracle on the same seeded inputs and against the committed golden vectors produced by
+the reference's own sources.  Tolerances are BASELINE.json's: singular values 1e-10 relative, modes
+|<u_ref,u>| >= 1 - 1e-8 for well separated modes, reconstruction RMSE equal to 1e-10."""
+import ctypes, glob, os
+import numpy as np
+import pytest
+import torch
+
+import pod_oracle as po
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+SIG_TOL = 1e-10
+MODE_TOL = 1 - 1e-8
+RMSE_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def pl():
+    import pyloworder_b200
+    assert torch.cuda.is_available()
+    return pyloworder_b200
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def assert_svd_parity(ref, got, n_expected=None):
+    mt = po.compare_svd(*ref, *got)
+    assert mt["sigma_rel"] <= SIG_TOL, mt
+    assert mt["sigma_rel_each"] <= SIG_TOL, mt
+    assert mt["mode_min"] >= MODE_TOL, mt
+    assert mt["vmode_min"] >= MODE_TOL, mt
+    return mt
+
+
+# ---- golden vectors from the reference's own Python sources --------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_tsqr_svd_against_reference_golden(pl, path):
+    g = np.load(path)
+    A = g["A"]
+    U, S, V = [host(t) for t in pl.math.tsqr_svd(dev(A))]
+    assert U.shape == A.shape and S.shape == (A.shape[1],) and V.shape == (A.shape[1],) * 2
+    assert_svd_parity((g["tsqr_svd_P1_U"], g["tsqr_svd_P1_S"], g["tsqr_svd_P1_V"]), (U, S, V))
+    n = A.shape[1]
+    assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12
+    assert np.abs((U * S) @ V - A).max() <= 1e-12 * max(1.0, np.abs(A).max())
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_pod_pipeline_against_reference_golden(pl, path):
+    g = np.load(path)
+    A = g["A"]
+    Ad = dev(A)
+    U, S, V = pl.POD.run(Ad, remove_mean=True)
+    assert torch.equal(Ad, dev(A)), "POD.run must not modify X"
+    assert_svd_parity((g["pod_P1_U"], g["pod_P1_S"], g["pod_P1_V"]), (host(U), host(S), host(V)))
+    Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=1e-6)
+    assert Sr.shape[0] == int(g["pod_P1_N"])
+    Xr = pl.POD.reconstruct(Ur, Sr, Vr)
+    assert np.abs(host(Xr) - g["pod_P1_Xrec"]).max() <= 1e-10 * max(1.0, np.abs(A).max())
+    mean = pl.math.temporal_mean(Ad)
+    assert np.abs(host(mean) - g["pod_P1_mean"]).max() <= 4e-16 * A.shape[1] * np.abs(A).max()
+    Y = pl.math.subtract_mean(Ad, mean)
+    rm = pl.math.RMSE(Y, Xr)
+    assert abs(rm - float(g["pod_P1_rmse"])) <= RMSE_TOL
+
+
+# ---- seeded inputs against the oracle -------------------------------------------------------------
+CASES = [
+    (64, 64, "rand"),          # m == n
+    (33, 1, "rand"),           # single column
+    (1000, 2, "rand"),
+    (4097, 31, "rand"),        # odd n, ragged m
+    (2500, 32, "synth"),
+    (40000, 64, "synth"),      # cfg5 twin (n = 64)
+    (89351, 151, "synth"),     # cfg1 at full size
+    (60000, 256, "synth"),     # cfg3 twin (n = 256)
+    (20000, 512, "synth"),     # cfg2 twin (n = 512)
+    (12000, 999, "synth"),     # cfg4 twin (n = 999)
+    (30000, 100, "cond1e12"),
+]
+
+
+@pytest.mark.parametrize("m,n,kind", CASES, ids=lambda v: str(v))
+def test_tsqr_svd_against_oracle(pl, m, n, kind):
+    if kind == "rand":
+        A = synth.random_matrix(m, n, 17)
+    elif kind == "cond1e12":
+        A = synth.random_matrix(m, n, 5, cond=1e12)
+    else:
+        A = synth.snapshots(m, n, 2021)
+    U, S, V = [host(t) for t in pl.math.tsqr_svd(dev(A))]
+    Uo, So, Vo = po.tsqr_svd(A)
+    assert_svd_parity((Uo, So, Vo), (U, S, V))
+    assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12
+    assert np.linalg.norm((U * S) @ V - A) / np.linalg.norm(A) <= 1e-13 * np.sqrt(n) + 1e-14
+    assert np.all(np.diff(S) <= 0)
+
+
+@pytest.mark.parametrize("m,n", [(89351, 151), (50000, 256), (7000, 20)])
+def test_pod_run_remove_mean_against_oracle(pl, m, n):
+    X = synth.snapshots(m, n, 2023, nvars=1)
+    U, S, V = pl.POD.run(dev(X), remove_mean=True)
+    Uo, So, Vo = po.pod_run(X, remove_mean=True)
+    assert_svd_parity((Uo, So, Vo), (host(U), host(S), host(V)))
+    # centred data is rank deficient (rows sum to zero): the basis must still be orthonormal
+    Uh = host(U)
+    assert np.abs(Uh.T @ Uh - np.eye(n)).max() <= 1e-12
+    for r in (1e-6, 5, -0.9):
+        Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=r)
+        Xr = host(pl.POD.reconstruct(Ur, Sr, Vr))
+        Xo = po.reconstruct(*po.truncate(Uo, So, Vo, r=r))
+        assert Ur.shape[1] == Xo.shape[1] * 0 + po.truncate(Uo, So, Vo, r=r)[1].shape[0]
+        Y = po.subtract_mean(X, po.temporal_mean(X))
+        assert abs(po.RMSE(Y, Xr) - po.RMSE(Y, Xo)) <= RMSE_TOL
+    U2, S2, V2 = pl.POD.run(dev(X), remove_mean=False)
+    Uo2, So2, Vo2 = po.pod_run(X, remove_mean=False)
+    assert_svd_parity((Uo2, So2, Vo2), (host(U2), host(S2), host(V2)))
+
+
+def test_averaging_kernels(pl):
+    for m, n in ((1, 1), (5, 3), (1000, 37), (513, 64), (4000, 512), (100, 1000), (70000, 151)):
+        X = synth.snapshots(max(m, 2), n, 3)[:m]
+        mean = pl.math.temporal_mean(dev(X))
+        ref = po.temporal_mean(X)
+        assert np.abs(host(mean) - ref).max() <= 4e-16 * n * np.abs(X).max()
+        Y = pl.math.subtract_mean(dev(X), dev(ref))
+        assert np.array_equal(host(Y), po.subtract_mean(X, ref))            # one subtraction: bit exact
+        Yn = pl.math.subtract_mean(X, ref)                                   # numpy in -> numpy out
+        assert isinstance(Yn, np.ndarray) and np.array_equal(Yn, host(Y))
+        # the documented way to add the mean back (docs notebook: subtract_mean(X_POD, -1*mean))
+        Z = pl.math.subtract_mean(Y, -1 * dev(ref))
+        assert np.abs(host(Z) - X).max() <= 2e-16 * np.abs(X).max() * 2
+
+
+def test_matmul_vecmat_reconstruct(pl):
+    rng = np.random.default_rng(0)
+    for m, n, k in ((1000, 64, 64), (777, 151, 151), (5000, 512, 512), (300, 40, 7), (129, 33, 100), (1, 1, 1), (257, 999, 999)):
+        A = rng.standard_normal((m, k)); B = rng.standard_normal((k, n))
+        C = host(pl.math.matmul(dev(A), dev(B)))
+        assert np.abs(C - A @ B).max() <= 1e-13 * k * 10
+    v = rng.standard_normal(37); A = rng.standard_normal((37, 50))
+    assert np.array_equal(host(pl.math.vecmat(dev(v), dev(A))), po.vecmat(v, A))
+    # reconstruct on truncated (strided) views
+    U = rng.standard_normal((900, 40)); S = np.abs(rng.standard_normal(40)); V = rng.standard_normal((40, 60))
+    Ud, Sd, Vd = dev(U), dev(S), dev(V)
+    X = host(pl.POD.reconstruct(Ud[:, :7], Sd[:7], Vd[:7, :]))
+    assert np.abs(X - po.reconstruct(U[:, :7], S[:7], V[:7, :])).max() <= 1e-12
+
+
+def test_qr_and_svd_entry_points(pl):
+    A = synth.random_matrix(3000, 45, 1, cond=1e6)
+    Q, R = [host(t) for t in pl.math.qr(dev(A))]
+    assert np.allclose(np.tril(R, -1), 0)
+    assert np.abs(Q.T @ Q - np.eye(45)).max() <= 1e-13
+    assert np.abs(Q @ R - A).max() <= 1e-13 * np.abs(A).max() * 45
+    Rr = np.linalg.qr(A, mode="r")
+    assert np.abs(np.abs(R) - np.abs(Rr)).max() <= 1e-12 * np.abs(Rr).max()
+    Qt, Rt = [host(t) for t in pl.math.tsqr(dev(A))]
+    assert np.abs(Qt @ Rt - A).max() <= 1e-13 * np.abs(A).max() * 45
+    U, S, V = [host(t) for t in pl.math.svd(dev(R))]
+    So = np.linalg.svd(R, compute_uv=False)
+    assert np.max(np.abs(S - So) / So) <= 1e-10
+
+
+def test_error_behaviour(pl):
+    with pytest.raises(ValueError, match="at least n rows"):
+        pl.math.tsqr_svd(dev(np.zeros((3, 5))))
+    with pytest.raises(NotImplementedError):
+        pl.math.tsqr_svd(torch.zeros((10, 2), dtype=torch.float32, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        pl.POD.run(dev(np.ones((10, 2))), randomized=True)
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    rc = L.pl_tsqr_svd_f64(None, None, None, None, 3, 5, None, 0, None)
+    assert rc < 0
+
+
+def test_c_abi_host_entry_point(pl):
+    """pl_tsqr_svd_host_f64: same arguments as the reference's dtsqr_svd, host pointers."""
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    m, n = 5000, 48
+    A = synth.snapshots(m, n, 9)
+    U = np.zeros((m, n)); S = np.zeros(n); V = np.zeros((n, n))
+    rc = L.pl_tsqr_svd_host_f64(U.ctypes.data, S.ctypes.data, V.ctypes.data, A.ctypes.data, m, n)
+    assert rc == 0, L.pl_last_error()
+    assert_svd_parity(po.tsqr_svd(A), (U, S, V))
+    reflib = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libpylom_ref.so")
+    if os.path.exists(reflib):   # and against the reference's own compiled C, same call shape
+        R = ctypes.CDLL(reflib)
+        dp = ctypes.POINTER(ctypes.c_double)
+        U2 = np.zeros((m, n)); S2 = np.zeros(n); V2 = np.zeros((n, n))
+        assert R.dtsqr_svd(U2.ctypes.data_as(dp), S2.ctypes.data_as(dp), V2.ctypes.data_as(dp), A.ctypes.data_as(dp),
+                           ctypes.c_int(m), ctypes.c_int(n)) == 0
+        assert_svd_parity((U2, S2, V2), (U, S, V))
+
+
+def test_large_properties(pl):
+    """Size-independent properties at a size the CPU oracle would not finish quickly."""
+    m, n = 2_000_000, 64
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    A = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+    A[:, 5] = A[:, 4] * 2.0 + 1e-9 * A[:, 5]          # a nearly dependent column
+    U, S, V = pl.math.tsqr_svd(A)
+    I = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert float((U.T @ U - I).abs().max()) <= 1e-12
+    assert float((V @ V.T - I).abs().max()) <= 1e-12
+    assert float(((U * S) @ V - A).norm() / A.norm()) <= 1e-13
+    assert bool((S[:-1] >= S[1:]).all())
+    # linearity: scaling A scales S, leaves the modes (up to sign)
+    U2, S2, V2 = pl.math.tsqr_svd(A * 3.0)
+    assert float(((S2 - 3.0 * S).abs() / (3.0 * S)).max()) <= 1e-12
+    # idempotence of the projector on the range
+    X = pl.POD.reconstruct(U, S, V)
+    assert float((X - A).abs().max()) <= 1e-11
+
+
+def test_native_library_is_the_one_running(pl):
+    from pyloworder_b200 import _lib
+    before = _lib.lib().pl_launch_count()
+    pl.math.tsqr_svd(dev(synth.random_matrix(500, 10, 2)))
+    assert _lib.lib().pl_launch_count() > before
+    maps = open("/proc/self/maps").read()
+    assert "libpylom_b200.so" in maps

@@ -1,0 +1,131 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host layer has
+no CPU fallback, planner / partitioning logic, bench's device generator == oracle generator, and
+the multi-rank composition of tsqr_svd over gloo (world_size 2) with an injected CPU engine."""
+import ctypes, os, re, subprocess, sys, textwrap
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyloworder_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pylom_b200.h")).read()
+    declared = set(re.findall(r"\b(pl_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = ctypes.CDLL(_lib.libpath())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/pylom_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= declared
+    assert _lib.lib().pl_version() >= 100
+
+
+def test_workspace_query_and_argument_errors_without_gpu():
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    assert L.pl_qr_workspace_bytes(8_000_000, 512) > 8_000_000 * 512 * 8
+    assert L.pl_qr_workspace_bytes(0, 5) == 0
+    # bad shapes are rejected before any CUDA call
+    rc = L.pl_tsqr_svd_f64(None, None, None, None, 3, 5, None, 0, None)
+    assert rc < 0 and b"m >= n" in L.pl_last_error()
+    rc = L.pl_qr_factor_f64(None, None, None, 100, 10, 0, None, 0, None)
+    assert rc < 0 and b"workspace" in L.pl_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import pyloworder_b200 as pl
+    X = np.random.default_rng(0).standard_normal((64, 4))
+    for fn in (lambda: pl.POD.run(X), lambda: pl.math.tsqr_svd(X), lambda: pl.math.temporal_mean(X)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn()
+
+
+def test_worksplit_matches_oracle():
+    import pod_oracle as po
+    from pyloworder_b200.utils import worksplit
+    for m, P in ((10, 3), (89351, 8), (7, 7), (5, 8), (192_000_000, 8), (1000, 1)):
+        for r in range(P):
+            assert worksplit(0, m, r, P) == po.worksplit(0, m, r, P)
+
+
+def test_truncation_rule_matches_golden(golden_dir):
+    from pyloworder_b200.vmmath import compute_truncation_residual
+    import glob
+    for path in glob.glob(os.path.join(golden_dir, "*.npz")):
+        g = np.load(path)
+        S = g["tsqr_svd_P1_S"]
+        for r, N in zip(g["trunc_r"], g["trunc_N"]):
+            assert compute_truncation_residual(S, float(r)) == int(N)
+            assert compute_truncation_residual(torch.from_numpy(S), float(r)) == int(N)
+
+
+def test_bench_generator_matches_oracle_generator():
+    sys.path.insert(0, ROOT)
+    import bench, synth
+    X = bench.device_snapshots(torch, 5000, 24, 2022, 1000, 1400, torch.device("cpu"), chunk=150).numpy()
+    Y = synth.snapshots(5000, 24, 2022, 1000, 1400)
+    assert np.abs(X - Y).max() < 1e-13
+    # the noise term (1e-8 * hash) must be the same hash, not just the smooth part
+    assert np.abs((X - Y)).max() < 1e-8 * 1e-4
+
+
+GLOO_SCRIPT = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'oracle'))
+    import numpy as np, torch, torch.distributed as dist
+    import pod_oracle as po, synth
+    from pyloworder_b200.utils import parall
+    import importlib; plsvd = importlib.import_module('pyloworder_b200.vmmath.svd')
+
+    class CpuEngine:                      # test stand-in for the CUDA engine (numpy / LAPACK)
+        def __init__(self): self.store = {{}}
+        def factor(self, A, tag, center=False):
+            a = A.numpy(); mean = None
+            if center:
+                mean = a.mean(1); a = a - mean[:, None]
+            Q, R = np.linalg.qr(a); self.store[tag] = Q
+            return torch.from_numpy(R), (torch.from_numpy(mean) if center else None)
+        def apply_q(self, shape, W, tag, device):
+            Q = self.store[tag]
+            return torch.from_numpy(Q if W is None else Q @ W.numpy())
+        def svd(self, R):
+            U, S, V = np.linalg.svd(R.numpy()); return torch.from_numpy(U), torch.from_numpy(S), torch.from_numpy(V)
+        def tsqr_svd_single(self, A, center=False): raise AssertionError('single-rank path in a 2-rank run')
+        def allgather_rows(self, R): return parall.mpi_allgather_rows(R)
+
+    rank, size = parall.init_distributed('gloo')
+    assert size == 2 and parall.MPI_SIZE == 2
+    m, n = 901, 12
+    A = synth.snapshots(m, n, 5)
+    r0, r1 = parall.worksplit(0, m, rank, size)
+    U, S, V, mean = plsvd._tsqr_svd_dev(torch.from_numpy(A[r0:r1].copy()), center=True, engine=CpuEngine())
+    Ul, So, Vo = po.pod_run([A[slice(*po.worksplit(0, m, r, 2))] for r in range(2)], remove_mean=True)
+    mt = po.compare_svd(Ul[rank], So, Vo, U.numpy(), S.numpy(), V.numpy())
+    assert mt['sigma_rel'] < 1e-13, mt
+    assert mt['vmode_min'] > 1 - 1e-10, mt
+    # U is distributed: inner products need the sum over ranks
+    ip = np.einsum('ik,ik->k', Ul[rank], U.numpy())
+    ip = parall.mpi_reduce(ip, op='sum')
+    keep = So / So[0] > 1e-8
+    assert np.abs(np.abs(ip[keep]) - 1).max() < 1e-8, ip
+    Sg = [torch.zeros_like(S) for _ in range(2)]; dist.all_gather(Sg, S)
+    assert torch.equal(Sg[0], Sg[1])            # identical on all ranks
+    assert abs(float(parall.mpi_reduce(1.0)) - 2.0) < 1e-15
+    dist.barrier(); dist.destroy_process_group()
+    print('RANK_OK', rank)
+""")
+
+
+def test_two_rank_composition_over_gloo(tmp_path):
+    script = tmp_path / "gloo2.py"
+    script.write_text(GLOO_SCRIPT.format(root=ROOT))
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0)); port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout

@@ -10,9 +10,9 @@
 //     the NB carried rows Z stay in shared memory while the strip streams through);
 //   * the strips' NB-row tops are reduced by the same two kernels applied recursively
 //     (levels), so the whole factorisation is 2 kernel launches per (panel, level);
-//   * panel kernel  (caqr_panel_kernel):  Householder on [R; tile] with one row per thread,
-//     one batched 32-value warp transpose-reduction per column (norm, trailing products and the
-//     T-factor products come out of the same reduction), compact-WY T built on the fly;
+//   * panel kernel  (caqr_panel_kernel):  Householder on [R; tile], one column per lane,
+//     lane-local column inner products (norm, trailing products and the T-factor products
+//     come out of the same 32 FMA chains), compact-WY T built on the fly;
 //   * update kernel (caqr_update_kernel): W = V^T C, W' = op(T) W, C -= V W' as FP64 DMMA
 //     (mma.sync m16n8k16.f64) GEMMs out of shared memory, tile staged with cp.async.
 //
@@ -20,6 +20,7 @@
 #include "pl_common.cuh"
 #include "caqr.h"
 #include <vector>
+#include <cstdlib>
 
 namespace pl {
 
@@ -62,172 +63,265 @@ Plan make_plan(int64_t m, int64_t n) {
 // =============================================================================================
 // panel kernel
 // =============================================================================================
-// 160 threads: warp 0 holds the NB x NB pivot block Rp (lane = row), warps 1..4 hold the tile
-// body (one row per thread, the 32 panel entries of the row live in registers).
-__global__ void __launch_bounds__(160, 3)
+// 160 threads = 5 warps; each warp owns one NB x NB block of the stacked [Rp; tile] matrix
+// (warp 0: the pivot block Rp, warps 1..4: the four body blocks of the tile).  In the body warps
+// LANE k HOLDS COLUMN k of the block in registers (a[r], r = row inside the block); the pivot block
+// lives in shared memory (Rs) because it needs row access (the pivot row) as well.  With this layout
+//   * the column inner products x^T P_k of a Householder step are lane-local FMA chains (no shuffle
+//     reductions); the pivot column x is published once per step through shared memory and read
+//     back with broadcast 128-bit loads;
+//   * the same 32 lane-local products deliver the norm (lane j), the trailing update (lanes > j)
+//     and the compact-WY T-factor products (lanes < j);
+//   * global loads/stores of a block row are 256 contiguous bytes per warp;
+//   * the column loop is a RUNTIME loop (no register array is indexed by j), so the kernel is a few
+//     KB of code instead of 250 KB -- the fully unrolled first version was instruction-fetch bound.
+// Reflector columns are kept UNSCALED (u = x, pivot entry implied) during the 32 steps and scaled by
+// their 1/(alpha - beta) once at the end.
+__device__ __forceinline__ double fast_rsqrt(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double h = 0.5 * s;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  y = y * fma(-d, y, 2.0);
+  y = y * fma(-d, y, 2.0);
+  return y;
+}
+
+#ifdef PL_PANEL_TIMING
+__device__ unsigned long long g_panel_dbg[8];
+extern "C" int pl_debug_panel_read(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_panel_dbg, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_panel_dbg, z, sizeof(z));
+  return 0;
+}
+#define PT_MARK(k) do { long long _t = clock64(); if (lane == 0 && warp == PT_WARP) atomicAdd(&g_panel_dbg[k], (unsigned long long)(_t - tprev)); tprev = _t; } while (0)
+#else
+#define PT_MARK(k)
+#endif
+template <int MINB>
+__global__ void __launch_bounds__(160, MINB)
 caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, int64_t nblk, int64_t bs,
                   int64_t ntiles, int s, int upper, double* __restrict__ Tl, double* __restrict__ Vupl) {
+  __shared__ __align__(16) double xs[5][32];
   __shared__ double red[2][5][32];
-  __shared__ __align__(16) double prow[2][32];
-  __shared__ __align__(16) double wbuf[5][32];
+  __shared__ double prow[2][32];
+  __shared__ double Rs[32][33];      // pivot block (needs row AND column access -> shared memory)
   __shared__ double Ts[32][33];
+  __shared__ __align__(16) double zsm[32];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t0 = (int64_t)blockIdx.x * s;
   const int64_t pivblk = t0 * G;
-  double a[32];
+  double a[32];          // body warps: column `lane` of this warp's NB x NB block
+  double mysc = 0.0;
 
-  // pivot block -> warp 0
-  if (warp == 0) {
-    const double2* src = reinterpret_cast<const double2*>(Vb + (row0 + pivblk * bs + lane) * ld + col0);
-#pragma unroll
-    for (int k = 0; k < 16; k++) { double2 v = src[k]; a[2 * k] = v.x; a[2 * k + 1] = v.y; }
-    if (upper) {
-#pragma unroll
-      for (int k = 0; k < 32; k++) if (k < lane) a[k] = 0.0;
+  if (warp == 0) {   // pivot block -> shared memory (row-wise, coalesced)
+    const double* src = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) {
+      const double v = src[(int64_t)r * ld];
+      Rs[r][lane] = (upper && r > lane) ? 0.0 : v;
     }
   }
 
   for (int i = 0; i < s; i++) {
     const int64_t t = t0 + i;
     if (t >= ntiles) break;
-    // ---- load the body rows of this tile
+    const bool dense_piv = (i == 0);          // later tiles see the carried triangle (x = 0 in the pivot block)
+    const int twarp = dense_piv ? 4 : 0;      // the warp with spare time builds T
     int q = -1;
     if (warp >= 1) q = (i == 0) ? (warp <= 3 ? warp : -1) : (warp - 1);
     const int64_t kblk = t * G + q;
     const bool valid = (q >= 0) && (kblk < nblk);
-    double* rowp = Vb + (row0 + (valid ? kblk : 0) * bs + lane) * ld + col0;
+    double* blkp = Vb + (row0 + (valid ? kblk : 0) * bs) * ld + col0 + lane;
     if (warp >= 1) {
       if (valid) {
-        const double2* src = reinterpret_cast<const double2*>(rowp);
 #pragma unroll
-        for (int k = 0; k < 16; k++) { double2 v = src[k]; a[2 * k] = v.x; a[2 * k + 1] = v.y; }
+        for (int r = 0; r < 32; r++) a[r] = blkp[(int64_t)r * ld];
         if (upper) {
 #pragma unroll
-          for (int k = 0; k < 32; k++) if (k < lane) a[k] = 0.0;
+          for (int r = 0; r < 32; r++) if (r > lane) a[r] = 0.0;
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 32; k++) a[k] = 0.0;
+        for (int r = 0; r < 32; r++) a[r] = 0.0;
       }
     }
     for (int e = threadIdx.x; e < 32 * 33; e += 160) (&Ts[0][0])[e] = 0.0;
+    mysc = 0.0;
     __syncthreads();
 
-    // ---- 32 Householder steps
-#pragma unroll
+#ifdef PL_PANEL_TIMING
+    long long tprev = clock64();
+#endif
+#pragma unroll 1
     for (int j = 0; j < 32; j++) {
       const int buf = j & 1;
-      double x;
-      if (warp == 0) x = (lane > j) ? a[j] : 0.0; else x = a[j];
-      // batched reduction of x * a[k], k = 0..31 (lane k ends up with the warp total of index k)
-      double v[16];
-      {
-        const bool up = lane & 16;
+      PT_MARK(0);
+      // 1. publish column j of this warp's block and form the lane-local inner products x^T P_lane
+      double dsum = 0.0;
+      if (warp == 0) {
+        prow[buf][lane] = Rs[j][lane];
+        if (dense_piv) {
+          xs[0][lane] = (lane > j) ? Rs[lane][j] : 0.0;     // only rows below the pivot are active
+          __syncwarp();
+          double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          double lo = x * a[k], hi = x * a[k + 16];
-          double send = up ? lo : hi, keep = up ? hi : lo;
-          v[k] = keep + __shfl_xor_sync(FULL, send, 16);
+          for (int r = 0; r < 32; r += 4) {
+            const double2 xa = *reinterpret_cast<const double2*>(&xs[0][r]);
+            const double2 xb = *reinterpret_cast<const double2*>(&xs[0][r + 2]);
+            d0 = fma(xa.x, Rs[r][lane], d0); d1 = fma(xa.y, Rs[r + 1][lane], d1);
+            d2 = fma(xb.x, Rs[r + 2][lane], d2); d3 = fma(xb.y, Rs[r + 3][lane], d3);
+          }
+          dsum = (d0 + d1) + (d2 + d3);
         }
-      }
+      } else {
+        if (lane == j) {
 #pragma unroll
-      for (int off = 8; off >= 1; off >>= 1) {
-        const bool up = lane & off;
-#pragma unroll
-        for (int k = 0; k < off; k++) {
-          double send = up ? v[k] : v[k + off], keep = up ? v[k + off] : v[k];
-          v[k] = keep + __shfl_xor_sync(FULL, send, off);
+          for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2*>(&xs[warp][r]) = make_double2(a[r], a[r + 1]);
         }
-      }
-      red[buf][warp][lane] = v[0];
-      if (warp == 0 && lane == j) {
+        __syncwarp();
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, d5 = 0.0, d6 = 0.0, d7 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) reinterpret_cast<double2*>(prow[buf])[k] = make_double2(a[2 * k], a[2 * k + 1]);
+        for (int r = 0; r < 32; r += 8) {
+          const double2 xa = *reinterpret_cast<const double2*>(&xs[warp][r]);
+          const double2 xb = *reinterpret_cast<const double2*>(&xs[warp][r + 2]);
+          const double2 xc = *reinterpret_cast<const double2*>(&xs[warp][r + 4]);
+          const double2 xd = *reinterpret_cast<const double2*>(&xs[warp][r + 6]);
+          d0 = fma(xa.x, a[r], d0); d1 = fma(xa.y, a[r + 1], d1);
+          d2 = fma(xb.x, a[r + 2], d2); d3 = fma(xb.y, a[r + 3], d3);
+          d4 = fma(xc.x, a[r + 4], d4); d5 = fma(xc.y, a[r + 5], d5);
+          d6 = fma(xd.x, a[r + 6], d6); d7 = fma(xd.y, a[r + 7], d7);
+        }
+        dsum = ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
       }
+      PT_MARK(1);
+      red[buf][warp][lane] = dsum;
       __syncthreads();
-      const double tot = red[buf][0][lane] + red[buf][1][lane] + red[buf][2][lane] + red[buf][3][lane] + red[buf][4][lane];
+      PT_MARK(2);
+      const double tot = (red[buf][0][lane] + red[buf][1][lane]) + (red[buf][2][lane] + red[buf][3][lane]) + red[buf][4][lane];
       const double alpha = prow[buf][j];
       const double sigma2 = __shfl_sync(FULL, tot, j);
       double beta = alpha, tau = 0.0, scale = 0.0;
       if (sigma2 != 0.0) {
-        beta = -copysign(sqrt(alpha * alpha + sigma2), alpha);
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
-      }
-      const double zz = prow[buf][lane] + scale * tot;   // lane>j: pre-w ; lane<j: T-factor product
-      wbuf[warp][lane] = (lane > j) ? tau * zz : 0.0;
-      __syncwarp();
-      double vr;
-      if (warp == 0) vr = (lane > j) ? x * scale : ((lane == j) ? 1.0 : 0.0); else vr = x * scale;
-      if (j < 31) {
-#pragma unroll
-        for (int k = (j + 2) & ~1; k < 32; k += 2) {
-          double2 w2 = *reinterpret_cast<const double2*>(&wbuf[warp][k]);
-          a[k] -= vr * w2.x; a[k + 1] -= vr * w2.y;
+        const double s2 = fma(alpha, alpha, sigma2);
+        if (s2 > 1e-280 && s2 < 1e280) {
+          const double rinv = fast_rsqrt(s2);            // 1 / |beta|
+          const double nrm = s2 * rinv;
+          beta = -copysign(nrm, alpha);
+          const double dd = alpha - beta;
+          scale = fast_rcp(dd);
+          tau = dd * copysign(rinv, alpha);              // (beta - alpha) / beta
+        } else {
+          beta = -copysign(sqrt(s2), alpha);
+          tau = (beta - alpha) / beta;
+          scale = 1.0 / (alpha - beta);
         }
-        if (((j + 1) & 1)) a[j + 1] -= vr * wbuf[warp][j + 1];
       }
-      if (warp == 0) { if (lane > j) a[j] = vr; else if (lane == j) a[j] = beta; } else a[j] = vr;
-      // compact-WY T, column j (warp 4): T[0:j,j] = -tau * T[0:j,0:j] * z,  T[j][j] = tau
-      if (warp == 4) {
-        double acc = 0.0;
+      if (lane == j) mysc = scale;
+      PT_MARK(3);
+      const double zz = fma(scale, tot, prow[buf][lane]);
+      const double w = (lane > j) ? tau * zz : 0.0;
+      // 2. trailing update of this lane's column: P[r][lane] -= (x_r * scale) * w
+      const double sw = scale * w;
+      if (warp == 0) {
+        if (dense_piv) {
 #pragma unroll
-        for (int l = 0; l < j; l++) {
-          double zl = __shfl_sync(FULL, zz, l);
-          acc += Ts[lane][l] * zl;
+          for (int r = 0; r < 32; r += 2) {
+            const double2 xa = *reinterpret_cast<const double2*>(&xs[0][r]);
+            Rs[r][lane] = fma(-xa.x, sw, Rs[r][lane]);
+            Rs[r + 1][lane] = fma(-xa.y, sw, Rs[r + 1][lane]);
+          }
         }
+        Rs[j][lane] = (lane == j) ? beta : (Rs[j][lane] - w);    // pivot row (v = 1), new diagonal
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+          const double2 xa = *reinterpret_cast<const double2*>(&xs[warp][r]);
+          const double2 xb = *reinterpret_cast<const double2*>(&xs[warp][r + 2]);
+          a[r] = fma(-xa.x, sw, a[r]); a[r + 1] = fma(-xa.y, sw, a[r + 1]);
+          a[r + 2] = fma(-xb.x, sw, a[r + 2]); a[r + 3] = fma(-xb.y, sw, a[r + 3]);
+        }
+      }
+      PT_MARK(4);
+      // 3. compact-WY T, column j:  T[0:j,j] = -tau * T[0:j,0:j] * z ,  T[j][j] = tau.
+      //    Columns >= j of Ts are still zero, so the sum runs over all 32 entries (static unroll).
+      if (warp == twarp) {
+        zsm[lane] = (lane < j) ? mysc * zz : 0.0;
+        __syncwarp();
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+        for (int l = 0; l < 32; l += 4) {
+          const double2 za = *reinterpret_cast<const double2*>(&zsm[l]);
+          const double2 zb = *reinterpret_cast<const double2*>(&zsm[l + 2]);
+          c0 = fma(Ts[lane][l], za.x, c0); c1 = fma(Ts[lane][l + 1], za.y, c1);
+          c2 = fma(Ts[lane][l + 2], zb.x, c2); c3 = fma(Ts[lane][l + 3], zb.y, c3);
+        }
+        const double acc = (c0 + c1) + (c2 + c3);
         if (lane < j) Ts[lane][j] = -tau * acc;
         if (lane == j) Ts[lane][j] = tau;
-        __syncwarp();
       }
       __syncwarp();
+      PT_MARK(5);
     }
     __syncthreads();
+    PT_MARK(6);
 
-    // ---- write reflectors, T
+    // ---- scale the reflector columns, write reflectors and T
+    if (warp == 0) {
+      if (dense_piv) {
+#pragma unroll 8
+        for (int r = 1; r < 32; r++) if (r > lane) Rs[r][lane] *= mysc;
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; r++) a[r] *= mysc;
+    }
     double* Tt = Tl + t * (NB * NB);
     for (int e = threadIdx.x; e < NB * NB; e += 160) Tt[e] = Ts[e >> 5][e & 31];
     if (!upper) {
       if (warp >= 1 && valid) {
-        double2* dst = reinterpret_cast<double2*>(rowp);
 #pragma unroll
-        for (int k = 0; k < 16; k++) dst[k] = make_double2(a[2 * k], a[2 * k + 1]);
+        for (int r = 0; r < 32; r++) blkp[(int64_t)r * ld] = a[r];
       }
       if (warp == 0 && i == 0) {   // strictly-lower part of the pivot block = reflector entries
-        double* dst = Vb + (row0 + pivblk * bs + lane) * ld + col0;
-#pragma unroll
-        for (int k = 0; k < 32; k++) if (k < lane) dst[k] = a[k];
+        double* dst = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
+#pragma unroll 8
+        for (int r = 1; r < 32; r++) if (r > lane) dst[(int64_t)r * ld] = Rs[r][lane];
       }
     } else {
       double* Vt = Vupl + t * (TB * NB);
       if (warp >= 1 && q >= 0) {   // body block q of the tile (zeros when the block is missing)
-        double2* dst = reinterpret_cast<double2*>(Vt + (q * NB + lane) * NB);
+        double* dst = Vt + (q * NB) * NB + lane;
 #pragma unroll
-        for (int k = 0; k < 16; k++) dst[k] = make_double2(a[2 * k], a[2 * k + 1]);
+        for (int r = 0; r < 32; r++) dst[r * NB] = a[r];
       }
-      if (i == 0) {
-        if (warp == 0) {           // explicit unit-lower pivot block
-          double* dst = Vt + lane * NB;
-#pragma unroll
-          for (int k = 0; k < 32; k++) dst[k] = (k < lane) ? a[k] : ((k == lane) ? 1.0 : 0.0);
-        }
-        if (warp == 4) {           // tile 0 has only 3 body blocks; block slot 0 is the pivot
-          // nothing: slots 1..3 written by warps 1..3
-        }
+      if (i == 0 && warp == 0) {   // explicit unit-lower pivot block
+        double* dst = Vt + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) dst[r * NB] = (r > lane) ? Rs[r][lane] : ((r == lane) ? 1.0 : 0.0);
       }
     }
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < 32; k++) if (k < lane) a[k] = 0.0;   // carry only the triangle
+    if (warp == 0 && dense_piv) {
+#pragma unroll 8
+      for (int r = 1; r < 32; r++) if (r > lane) Rs[r][lane] = 0.0;   // carry only the triangle
     }
     __syncthreads();
   }
   // ---- R of the strip -> upper triangle of its pivot block
   if (warp == 0) {
-    double* dst = Vb + (row0 + pivblk * bs + lane) * ld + col0;
-#pragma unroll
-    for (int k = 0; k < 32; k++) if (k >= lane) dst[k] = a[k];
+    double* dst = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) if (r <= lane) dst[(int64_t)r * ld] = Rs[r][lane];
   }
 }
 
@@ -265,74 +359,90 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
   if (t0 + cnt > A.ntiles) cnt = (int)(A.ntiles - t0);
   const int64_t pivrow = A.row0 + t0 * G * A.bs;
 
+  // ---- per-thread staging geometry, hoisted out of the tile loop: this thread copies the 16-byte
+  //      piece (row r_lo [+16], columns c2..c2+1) of every NB x NB slab.
+  const int r_lo = tid >> 4, c2 = (tid & 15) * 2;
+  const bool upper = A.upper != 0;
+  const int64_t v_tile = upper ? (int64_t)TB * NB : (int64_t)G * A.bs * A.ld;
+  const int64_t v_q = upper ? (int64_t)NB * NB : A.bs * A.ld;
+  const int64_t v_h = upper ? (int64_t)16 * NB : 16 * A.ld;
+  const double* vbase = upper ? (A.Vupl + r_lo * NB + c2) : (A.Vb + (A.row0 + r_lo) * A.ld + A.col0 + c2);
+  const int64_t c_tile = (int64_t)G * A.bs * ldc, c_q = A.bs * ldc, c_h = 16 * ldc;
+  double* cbase = Cb + (A.row0 + r_lo) * ldc + coff + c2;
+  const double* tbase = A.Tl + r_lo * NB + c2;
+
   if (!A.forward) {   // backward: carried rows come from memory
-    for (int e = tid; e < NB * 16; e += 256) {
-      int r = e >> 4, c2 = (e & 15) * 2;
-      cp_async16(&S.Zs[r][c2], Cb + (pivrow + r) * ldc + coff + c2, true);
-    }
+    const double* zsrc = Cb + (pivrow + r_lo) * ldc + coff + c2;
+    cp_async16(&S.Zs[r_lo][c2], zsrc, true);
+    cp_async16(&S.Zs[r_lo + 16][c2], zsrc + c_h, true);
   }
+
+  // GEMM role of this warp
+  const int mb = warp >> 2, ng = warp & 3;     // GEMM1 / T-step: (m16 block, n8 group) of the NB x NB W
+  const int gq = warp >> 1, gh = warp & 1;     // GEMM2: (slab, column half)
 
   for (int it = 0; it < cnt; it++) {
     const int i = A.forward ? it : (cnt - 1 - it);
     const int64_t t = t0 + i;
     const bool first = (i == 0);
     // ---- stage V, C, T of this tile
-    for (int e = tid; e < G * NB * 16; e += 256) {
-      const int q = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
-      const int64_t kblk = t * G + q;
-      const bool valid = kblk < A.nblk;
-      const int64_t grow = A.row0 + (valid ? kblk : 0) * A.bs + r;
-      const double* vsrc = A.upper ? (A.Vupl + (t * TB + q * NB + r) * NB + c2)
-                                   : (A.Vb + grow * A.ld + A.col0 + c2);
-      cp_async16(&S.Vs[q][r][c2], vsrc, valid || A.upper);
-      if (first && q == 0) {
-        if (A.forward) cp_async16(&S.Zs[r][c2], Cb + grow * ldc + coff + c2, true);
-      } else {
-        cp_async16(&S.Cs[q][r][c2], Cb + grow * ldc + coff + c2, valid);
-      }
-    }
     {
-      const double* Tt = A.Tl + t * (NB * NB);
-      for (int e = tid; e < NB * 16; e += 256) {
-        int r = e >> 4, c2 = (e & 15) * 2;
-        cp_async16(&S.Ts[r][c2], Tt + r * NB + c2, true);
+      const double* vp = vbase + t * v_tile;
+      double* cp = cbase + t * c_tile;
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        const bool valid = (t * G + q) < A.nblk;
+        const double* vs = valid ? (vp + q * v_q) : vp;
+        const double* cs = valid ? (cp + q * c_q) : cp;
+        const bool vok = valid || upper;
+        cp_async16(&S.Vs[q][r_lo][c2], vs, vok);
+        cp_async16(&S.Vs[q][r_lo + 16][c2], vs + v_h, vok);
+        if (q == 0 && first) {
+          if (A.forward) { cp_async16(&S.Zs[r_lo][c2], cs, true); cp_async16(&S.Zs[r_lo + 16][c2], cs + c_h, true); }
+        } else {
+          cp_async16(&S.Cs[q][r_lo][c2], cs, valid);
+          cp_async16(&S.Cs[q][r_lo + 16][c2], cs + c_h, valid);
+        }
       }
+      const double* tp = tbase + t * (NB * NB);
+      cp_async16(&S.Ts[r_lo][c2], tp, true);
+      cp_async16(&S.Ts[r_lo + 16][c2], tp + 16 * NB, true);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (first && !A.upper) {   // explicit unit-lower pivot block from the in-place storage
+    if (first && !upper) {   // explicit unit-lower pivot block from the in-place storage
       for (int e = tid; e < NB * NB; e += 256) {
         int r = e >> 5, c = e & 31;
         if (c > r) S.Vs[0][r][c] = 0.0; else if (c == r) S.Vs[0][r][c] = 1.0;
       }
       __syncthreads();
     }
+    const double (*C0)[SP] = first ? S.Zs : S.Cs[0];   // slab 0 of the first tile is the carried block
 
-    // ---- GEMM1: W = V^T C (+ Z)      W is NB x NB: warp -> (m16 block mb, n8 group ng)
-    const int mb = warp >> 2, ng = warp & 3;
+    // ---- GEMM1: W = V^T C (+ Z)      two independent accumulator chains (even / odd k16 steps)
     {
-      double acc[4] = {0, 0, 0, 0};
+      double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int q = 0; q < G; q++) {
-        const double (*Cq)[SP] = (first && q == 0) ? S.Zs : S.Cs[q];
+        const double (*Cq)[SP] = (q == 0) ? C0 : S.Cs[q];
+        double fa[8], fb[4];
 #pragma unroll
-        for (int kk = 0; kk < 2; kk++) {
-          double fa[8], fb[4];
+        for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1)][16 * mb + g + 8 * (x & 1)];
 #pragma unroll
-          for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16 * kk][16 * mb + g + 8 * (x & 1)];
+        for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x][8 * ng + g];
+        mma16816(acc0, fa, fb);
 #pragma unroll
-          for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16 * kk][8 * ng + g];
-          mma16816(acc, fa, fb);
-        }
+        for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16][16 * mb + g + 8 * (x & 1)];
+#pragma unroll
+        for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16][8 * ng + g];
+        mma16816(acc1, fa, fb);
       }
       const int r = 16 * mb + g, c = 8 * ng + 2 * t4;
-      if (!first) {
-        acc[0] += S.Zs[r][c]; acc[1] += S.Zs[r][c + 1];
-        acc[2] += S.Zs[r + 8][c]; acc[3] += S.Zs[r + 8][c + 1];
-      }
-      *reinterpret_cast<double2*>(&S.Ws[r][c]) = make_double2(acc[0], acc[1]);
-      *reinterpret_cast<double2*>(&S.Ws[r + 8][c]) = make_double2(acc[2], acc[3]);
+      double2 z01 = make_double2(0.0, 0.0), z23 = make_double2(0.0, 0.0);
+      if (!first) { z01 = *reinterpret_cast<const double2*>(&S.Zs[r][c]); z23 = *reinterpret_cast<const double2*>(&S.Zs[r + 8][c]); }
+      *reinterpret_cast<double2*>(&S.Ws[r][c]) = make_double2((acc0[0] + acc1[0]) + z01.x, (acc0[1] + acc1[1]) + z01.y);
+      *reinterpret_cast<double2*>(&S.Ws[r + 8][c]) = make_double2((acc0[2] + acc1[2]) + z23.x, (acc0[3] + acc1[3]) + z23.y);
     }
     __syncthreads();
     // ---- W' = op(T) W     forward: T^T, backward: T
@@ -341,10 +451,12 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
 #pragma unroll
       for (int kk = 0; kk < 2; kk++) {
         double fa[8], fb[4];
+        if (A.forward) {
 #pragma unroll
-        for (int x = 0; x < 8; x++) {
-          const int mm = 16 * mb + g + 8 * (x & 1), kq = t4 + 4 * (x >> 1) + 16 * kk;
-          fa[x] = A.forward ? S.Ts[kq][mm] : S.Ts[mm][kq];
+          for (int x = 0; x < 8; x++) fa[x] = S.Ts[t4 + 4 * (x >> 1) + 16 * kk][16 * mb + g + 8 * (x & 1)];
+        } else {
+#pragma unroll
+          for (int x = 0; x < 8; x++) fa[x] = S.Ts[16 * mb + g + 8 * (x & 1)][t4 + 4 * (x >> 1) + 16 * kk];
         }
 #pragma unroll
         for (int x = 0; x < 4; x++) fb[x] = S.Ws[t4 + 4 * x + 16 * kk][8 * ng + g];
@@ -353,32 +465,38 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       const int r = 16 * mb + g, c = 8 * ng + 2 * t4;
       *reinterpret_cast<double2*>(&S.Wp[r][c]) = make_double2(acc[0], acc[1]);
       *reinterpret_cast<double2*>(&S.Wp[r + 8][c]) = make_double2(acc[2], acc[3]);
+      if (!first) {   // carried block: Z -= W' (this warp owns exactly these entries of Z)
+        double2 z01 = *reinterpret_cast<const double2*>(&S.Zs[r][c]);
+        double2 z23 = *reinterpret_cast<const double2*>(&S.Zs[r + 8][c]);
+        z01.x -= acc[0]; z01.y -= acc[1]; z23.x -= acc[2]; z23.y -= acc[3];
+        *reinterpret_cast<double2*>(&S.Zs[r][c]) = z01;
+        *reinterpret_cast<double2*>(&S.Zs[r + 8][c]) = z23;
+      }
     }
     __syncthreads();
-    // ---- GEMM2: C -= V W'     warp -> (slab q, column half h)
+    // ---- GEMM2: C -= V W'     warp -> (slab gq, column half gh)
     {
-      const int q = warp >> 1, h = warp & 1;
-      const bool piv = first && q == 0;
-      double (*Cq)[SP] = piv ? S.Zs : S.Cs[q];
-      const int64_t kblk = t * G + q;
-      const bool valid = kblk < A.nblk;
+      const bool piv = first && gq == 0;
+      double (*Cq)[SP] = piv ? S.Zs : S.Cs[gq];
+      const bool valid = (t * G + gq) < A.nblk;
+      double* crow = Cb + (A.row0 + (t * G + gq) * A.bs + g) * ldc + coff + 16 * gh + 2 * t4;
       double fa[2][2][8];
 #pragma unroll
       for (int m2 = 0; m2 < 2; m2++)
 #pragma unroll
         for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-          for (int x = 0; x < 8; x++) fa[m2][kk][x] = S.Vs[q][16 * m2 + g + 8 * (x & 1)][t4 + 4 * (x >> 1) + 16 * kk];
+          for (int x = 0; x < 8; x++) fa[m2][kk][x] = S.Vs[gq][16 * m2 + g + 8 * (x & 1)][t4 + 4 * (x >> 1) + 16 * kk];
 #pragma unroll
       for (int nn = 0; nn < 2; nn++) {
         double fb[2][4];
 #pragma unroll
         for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-          for (int x = 0; x < 4; x++) fb[kk][x] = -S.Wp[t4 + 4 * x + 16 * kk][16 * h + 8 * nn + g];
+          for (int x = 0; x < 4; x++) fb[kk][x] = -S.Wp[t4 + 4 * x + 16 * kk][16 * gh + 8 * nn + g];
 #pragma unroll
         for (int m2 = 0; m2 < 2; m2++) {
-          const int r = 16 * m2 + g, c = 16 * h + 8 * nn + 2 * t4;
+          const int r = 16 * m2 + g, c = 16 * gh + 8 * nn + 2 * t4;
           double2 c01 = *reinterpret_cast<const double2*>(&Cq[r][c]);
           double2 c23 = *reinterpret_cast<const double2*>(&Cq[r + 8][c]);
           double acc[4] = {c01.x, c01.y, c23.x, c23.y};
@@ -388,22 +506,20 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
             *reinterpret_cast<double2*>(&S.Zs[r][c]) = make_double2(acc[0], acc[1]);
             *reinterpret_cast<double2*>(&S.Zs[r + 8][c]) = make_double2(acc[2], acc[3]);
           } else if (valid) {
-            double* dst = Cb + (A.row0 + kblk * A.bs + r) * ldc + coff + c;
+            double* dst = crow + (int64_t)(16 * m2) * ldc + 8 * nn;
             *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
             *reinterpret_cast<double2*>(dst + 8 * ldc) = make_double2(acc[2], acc[3]);
           }
         }
       }
     }
-    if (!first) {
-      for (int e = tid; e < NB * NB; e += 256) { int r = e >> 5, c = e & 31; S.Zs[r][c] -= S.Wp[r][c]; }
-    }
     __syncthreads();
   }
   // ---- carried rows back to the pivot block rows
-  for (int e = tid; e < NB * 16; e += 256) {
-    int r = e >> 4, c2 = (e & 15) * 2;
-    *reinterpret_cast<double2*>(Cb + (pivrow + r) * ldc + coff + c2) = *reinterpret_cast<const double2*>(&S.Zs[r][c2]);
+  {
+    double* zdst = Cb + (pivrow + r_lo) * ldc + coff + c2;
+    *reinterpret_cast<double2*>(zdst) = *reinterpret_cast<const double2*>(&S.Zs[r_lo][c2]);
+    *reinterpret_cast<double2*>(zdst + c_h) = *reinterpret_cast<const double2*>(&S.Zs[r_lo + 16][c2]);
   }
 }
 
@@ -496,9 +612,19 @@ int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_
       const Level& L = P.panels[p][li];
       {
         ProfScope ps(PROF_PANEL, st);
-        caqr_panel_kernel<<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
-                                                               li > 0, Tws + L.t_off * (NB * NB),
-                                                               li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+        static const int occ = getenv("PL_PANEL_OCC") ? atoi(getenv("PL_PANEL_OCC")) : 3;
+        if (occ == 4)
+          caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
+                                                                  li > 0, Tws + L.t_off * (NB * NB),
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+        else if (occ == 2)
+          caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
+                                                                  li > 0, Tws + L.t_off * (NB * NB),
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+        else
+          caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
+                                                                  li > 0, Tws + L.t_off * (NB * NB),
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
       }
       PL_LAUNCH_CHECK();
       int rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);

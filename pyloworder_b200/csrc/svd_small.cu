@@ -11,6 +11,7 @@
 #include "pl_common.cuh"
 #include "caqr.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace pl {
 
@@ -57,6 +58,78 @@ __global__ void __launch_bounds__(128) jacobi_round_kernel(double* __restrict__ 
     gp[j] = cs * x - sn * y; gq[j] = sn * x + cs * y;
     double u = jp[j], v = jq[j];
     jp[j] = cs * u - sn * v; jq[j] = sn * u + cs * v;
+  }
+}
+
+// One whole sweep (ne-1 rounds) in a single cooperative launch.  ONE WARP owns one row pair of every
+// round: the two rows of G (and then of J) are held in registers (EPL elements per lane per row), the
+// three inner products are shuffle reductions, so a rotation reads and writes each element once and
+// needs no block barrier.  Rounds are separated by a grid-wide barrier (monotone counter in global
+// memory); rows move between SMs from round to round, so G and J are read with ld.global.cg (L2) and
+// never through a possibly stale L1 line.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+  }
+  __syncthreads();
+}
+
+constexpr int JW = 8;   // warps (row pairs) per CTA
+
+template <int EPL>
+__global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
+                                                               double tol, int* __restrict__ rotations, unsigned* bar) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * JW + (threadIdx.x >> 5);       // pair index inside a round
+  const bool have = i < ne / 2;
+  for (int round = 0; round < ne - 1; round++) {
+    int p = 0, q = 0;
+    if (have) {
+      if (i == 0) { p = ne - 1; q = round; }
+      else { p = (round + i) % (ne - 1); q = (round - i + (ne - 1)) % (ne - 1); }
+    }
+    if (have && p < n && q < n) {
+      if (p > q) { int tmp = p; p = q; q = tmp; }
+      double* gp = Gm + (int64_t)p * n; double* gq = Gm + (int64_t)q * n;
+      double x[EPL], y[EPL];
+      double a = 0, b = 0, c = 0;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const int j = lane + 32 * e;
+        x[e] = (j < n) ? __ldcg(gp + j) : 0.0;
+        y[e] = (j < n) ? __ldcg(gq + j) : 0.0;
+        a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); c = fma(x[e], y[e], c);
+      }
+      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+      if (!(c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b))) {
+        if (lane == 0) atomicAdd(rotations, 1);
+        const double zeta = (b - a) / (2.0 * c);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int j = lane + 32 * e;
+          if (j < n) { gp[j] = cs * x[e] - sn * y[e]; gq[j] = sn * x[e] + cs * y[e]; }
+        }
+        double* jp = J + (int64_t)p * n; double* jq = J + (int64_t)q * n;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int j = lane + 32 * e;
+          x[e] = (j < n) ? __ldcg(jp + j) : 0.0;
+          y[e] = (j < n) ? __ldcg(jq + j) : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int j = lane + 32 * e;
+          if (j < n) { jp[j] = cs * x[e] - sn * y[e]; jq[j] = sn * x[e] + cs * y[e]; }
+        }
+      }
+    }
+    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
   }
 }
 
@@ -108,13 +181,30 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   int sweeps = 0;
   if (ni > 1) {
     const int max_sweeps = 60;
+    // cooperative single-launch sweeps when all n/2 CTAs can be co-resident
+    int dev = 0, coop = 0, nsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int sweep_blocks = (ne / 2 + JW - 1) / JW;
+    void* sweep_fn = ni <= 128 ? (void*)jacobi_sweep_kernel<4> : ni <= 256 ? (void*)jacobi_sweep_kernel<8>
+                   : ni <= 512 ? (void*)jacobi_sweep_kernel<16> : (void*)jacobi_sweep_kernel<32>;
+    const bool use_coop = coop && ni <= 1024 && sweep_blocks <= nsm;
+    unsigned* bar = reinterpret_cast<unsigned*>(rot + 1);
     for (; sweeps < max_sweeps;) {
-      PL_CUDA(cudaMemsetAsync(rot, 0, sizeof(int), st));
-      for (int r = 0; r < ne - 1; r++) {
-        jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot);
+      PL_CUDA(cudaMemsetAsync(rot, 0, 2 * sizeof(int), st));
+      if (use_coop) {
+        double tol_ = tol; int ni_ = ni, ne_ = ne;
+        void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &rot, &bar};
+        PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));
+        count_launches(1);
+      } else {
+        for (int r = 0; r < ne - 1; r++) {
+          jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot);
+        }
+        PL_LAUNCH_CHECK();
+        count_launches(ne - 2);
       }
-      PL_LAUNCH_CHECK();
-      count_launches(ne - 2);
       int h = 0;
       PL_CUDA(cudaMemcpyAsync(&h, rot, sizeof(int), cudaMemcpyDeviceToHost, st));
       PL_CUDA(cudaStreamSynchronize(st));
@@ -129,6 +219,7 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   PL_LAUNCH_CHECK();
   count_launches(2);
   if (sweeps_out) *sweeps_out = sweeps;
+  if (getenv("PL_DEBUG")) fprintf(stderr, "[pl] svd_small n=%d sweeps=%d\n", ni, sweeps);
   return 0;
 }
 

@@ -1,0 +1,56 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/dist_check.py
+Compares the NCCL-composed tsqr_svd / POD.run with the CPU oracle run on the same row shards."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np, torch, torch.distributed as dist
+import pyloworder_b200 as pl
+import pod_oracle as po, synth
+
+rank, size = pl.utils.init_distributed("nccl")
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+ok = True
+for (m, n, remove_mean) in ((5000, 24, False), (40000, 151, True), (3001, 64, True), (size * 70, 64, False)):
+    X = synth.snapshots(m, n, 2021)
+    shards = [X[slice(*po.worksplit(0, m, r, size))] for r in range(size)]
+    r0, r1 = pl.utils.worksplit(0, m, rank, size)
+    Xd = torch.from_numpy(X[r0:r1].copy()).to(dev)
+    if remove_mean:
+        U, S, V = pl.POD.run(Xd, remove_mean=True)
+        Uo, So, Vo = po.pod_run(shards, remove_mean=True)
+    else:
+        U, S, V = pl.math.tsqr_svd(Xd)
+        Uo, So, Vo = po.tsqr_svd(shards)
+    Uh, Sh, Vh = U.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy()
+    sig = np.abs(Sh - So).max() / So[0]
+    keep = (So / So[0] >= 1e-8)
+    gaps = np.minimum(np.r_[np.inf, -np.diff(So)], np.r_[-np.diff(So), np.inf]) / So[0] >= 1e-6
+    sel = keep & gaps
+    ip = torch.from_numpy(np.einsum("ik,ik->k", Uo[rank], Uh)).to(dev)
+    dist.all_reduce(ip)
+    ipn = np.abs(ip.cpu().numpy())
+    vip = np.abs(np.einsum("ki,ki->k", Vo, Vh))
+    G = U.T @ U
+    dist.all_reduce(G)
+    orth = float((G - torch.eye(n, dtype=torch.float64, device=dev)).abs().max())
+    Sall = [torch.zeros_like(S) for _ in range(size)]
+    dist.all_gather(Sall, S)
+    same = all(torch.equal(Sall[0], s) for s in Sall)
+    Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=1e-6)
+    Xr = pl.POD.reconstruct(Ur, Sr, Vr)
+    Y = Xd - Xd.mean(1, keepdim=True) if remove_mean else Xd
+    rm = pl.math.RMSE(Y, Xr)
+    Ul = np.vstack(Uo); Xo = po.reconstruct(*po.truncate(Ul, So, Vo, r=1e-6))
+    Yo = np.vstack([s - s.mean(1, keepdims=True) for s in shards]) if remove_mean else X
+    rmo = po.RMSE(Yo, Xo)
+    good = sig <= 1e-10 and ipn[sel].min() >= 1 - 1e-8 and vip[sel].min() >= 1 - 1e-8 and orth <= 1e-12 and same and abs(rm - rmo) <= 1e-10
+    ok &= bool(good)
+    if rank == 0:
+        print(f"P={size} {m}x{n} mean={remove_mean}: sigma_rel={sig:.2e} mode_min={ipn[sel].min():.12f} vmode_min={vip[sel].min():.12f} "
+              f"orth={orth:.2e} S_identical={same} rmse={rm:.3e}/{rmo:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+dist.barrier()
+if rank == 0:
+    print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

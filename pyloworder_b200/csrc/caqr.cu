@@ -110,7 +110,7 @@ template <int MINB>
 __global__ void __launch_bounds__(160, MINB)
 caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, int64_t nblk, int64_t bs,
                   int64_t ntiles, int s, int upper, double* __restrict__ Tl, double* __restrict__ Vupl) {
-  __shared__ __align__(16) double xs[5][32];
+  __shared__ __align__(16) double xs[2][5][32];   // pivot column of step j (buffer j&1), pre-published during step j-1
   __shared__ double red[2][5][32];
   __shared__ double prow[2][32];
   __shared__ double Rs[32][33];      // pivot block (needs row AND column access -> shared memory)
@@ -157,6 +157,10 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
     }
     for (int e = threadIdx.x; e < 32 * 33; e += 160) (&Ts[0][0])[e] = 0.0;
     mysc = 0.0;
+    if (warp >= 1 && lane == 0) {   // column 0 of the body blocks for step 0 (later columns are pre-published)
+#pragma unroll
+      for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2*>(&xs[0][warp][r]) = make_double2(a[r], a[r + 1]);
+    }
     __syncthreads();
 
 #ifdef PL_PANEL_TIMING
@@ -171,31 +175,26 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
       if (warp == 0) {
         prow[buf][lane] = Rs[j][lane];
         if (dense_piv) {
-          xs[0][lane] = (lane > j) ? Rs[lane][j] : 0.0;     // only rows below the pivot are active
+          xs[buf][0][lane] = (lane > j) ? Rs[lane][j] : 0.0;     // only rows below the pivot are active
           __syncwarp();
           double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
           for (int r = 0; r < 32; r += 4) {
-            const double2 xa = *reinterpret_cast<const double2*>(&xs[0][r]);
-            const double2 xb = *reinterpret_cast<const double2*>(&xs[0][r + 2]);
+            const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][0][r]);
+            const double2 xb = *reinterpret_cast<const double2*>(&xs[buf][0][r + 2]);
             d0 = fma(xa.x, Rs[r][lane], d0); d1 = fma(xa.y, Rs[r + 1][lane], d1);
             d2 = fma(xb.x, Rs[r + 2][lane], d2); d3 = fma(xb.y, Rs[r + 3][lane], d3);
           }
           dsum = (d0 + d1) + (d2 + d3);
         }
       } else {
-        if (lane == j) {
-#pragma unroll
-          for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2*>(&xs[warp][r]) = make_double2(a[r], a[r + 1]);
-        }
-        __syncwarp();
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, d5 = 0.0, d6 = 0.0, d7 = 0.0;
 #pragma unroll
         for (int r = 0; r < 32; r += 8) {
-          const double2 xa = *reinterpret_cast<const double2*>(&xs[warp][r]);
-          const double2 xb = *reinterpret_cast<const double2*>(&xs[warp][r + 2]);
-          const double2 xc = *reinterpret_cast<const double2*>(&xs[warp][r + 4]);
-          const double2 xd = *reinterpret_cast<const double2*>(&xs[warp][r + 6]);
+          const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][warp][r]);
+          const double2 xb = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 2]);
+          const double2 xc = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 4]);
+          const double2 xd = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 6]);
           d0 = fma(xa.x, a[r], d0); d1 = fma(xa.y, a[r + 1], d1);
           d2 = fma(xb.x, a[r + 2], d2); d3 = fma(xb.y, a[r + 3], d3);
           d4 = fma(xc.x, a[r + 4], d4); d5 = fma(xc.y, a[r + 5], d5);
@@ -214,12 +213,23 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
       if (sigma2 != 0.0) {
         const double s2 = fma(alpha, alpha, sigma2);
         if (s2 > 1e-280 && s2 < 1e280) {
-          const double rinv = fast_rsqrt(s2);            // 1 / |beta|
-          const double nrm = s2 * rinv;
+          // |beta| = sqrt(s2), scale = 1/(alpha - beta) = sgn/(|alpha| + |beta|), tau = (|alpha| + |beta|)/|beta|.
+          // The reciprocal is seeded from the UNREFINED rsqrt so that its MUFU overlaps the rsqrt Newton steps.
+          double y, rc;
+          asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s2));
+          const double aa = fabs(alpha);
+          const double dd0 = fma(s2, y, aa);
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dd0));
+          const double h = 0.5 * s2;
+          y = y * fma(-h * y, y, 1.5);
+          y = y * fma(-h * y, y, 1.5);                   // 1 / |beta|   (2^-22 -> 2^-43 -> full)
+          const double nrm = s2 * y;
+          const double dd = aa + nrm;
+          rc = rc * fma(-dd, rc, 2.0);
+          rc = rc * fma(-dd, rc, 2.0);                   // 1 / (|alpha| + |beta|)
           beta = -copysign(nrm, alpha);
-          const double dd = alpha - beta;
-          scale = fast_rcp(dd);
-          tau = dd * copysign(rinv, alpha);              // (beta - alpha) / beta
+          scale = copysign(rc, alpha);
+          tau = dd * y;
         } else {
           beta = -copysign(sqrt(s2), alpha);
           tau = (beta - alpha) / beta;
@@ -236,19 +246,24 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
         if (dense_piv) {
 #pragma unroll
           for (int r = 0; r < 32; r += 2) {
-            const double2 xa = *reinterpret_cast<const double2*>(&xs[0][r]);
+            const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][0][r]);
             Rs[r][lane] = fma(-xa.x, sw, Rs[r][lane]);
             Rs[r + 1][lane] = fma(-xa.y, sw, Rs[r + 1][lane]);
           }
         }
         Rs[j][lane] = (lane == j) ? beta : (Rs[j][lane] - w);    // pivot row (v = 1), new diagonal
       } else {
+        const bool next = (lane == j + 1);      // this lane owns the next pivot column: pre-publish it
 #pragma unroll
         for (int r = 0; r < 32; r += 4) {
-          const double2 xa = *reinterpret_cast<const double2*>(&xs[warp][r]);
-          const double2 xb = *reinterpret_cast<const double2*>(&xs[warp][r + 2]);
+          const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][warp][r]);
+          const double2 xb = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 2]);
           a[r] = fma(-xa.x, sw, a[r]); a[r + 1] = fma(-xa.y, sw, a[r + 1]);
           a[r + 2] = fma(-xb.x, sw, a[r + 2]); a[r + 3] = fma(-xb.y, sw, a[r + 3]);
+          if (next) {
+            *reinterpret_cast<double2*>(&xs[buf ^ 1][warp][r]) = make_double2(a[r], a[r + 1]);
+            *reinterpret_cast<double2*>(&xs[buf ^ 1][warp][r + 2]) = make_double2(a[r + 2], a[r + 3]);
+          }
         }
       }
       PT_MARK(4);

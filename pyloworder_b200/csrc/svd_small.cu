@@ -95,15 +95,19 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
     if (have && p < n && q < n) {
       if (p > q) { int tmp = p; p = q; q = tmp; }
       double* gp = Gm + (int64_t)p * n; double* gq = Gm + (int64_t)q * n;
-      double x[EPL], y[EPL];
+      double* jp = J + (int64_t)p * n; double* jq = J + (int64_t)q * n;
+      double x[EPL], y[EPL], u[EPL], v[EPL];
       double a = 0, b = 0, c = 0;
 #pragma unroll
-      for (int e = 0; e < EPL; e++) {
+      for (int e = 0; e < EPL; e++) {       // all four rows are requested up front (one L2 round trip)
         const int j = lane + 32 * e;
         x[e] = (j < n) ? __ldcg(gp + j) : 0.0;
         y[e] = (j < n) ? __ldcg(gq + j) : 0.0;
-        a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); c = fma(x[e], y[e], c);
+        u[e] = (j < n) ? __ldcg(jp + j) : 0.0;
+        v[e] = (j < n) ? __ldcg(jq + j) : 0.0;
       }
+#pragma unroll
+      for (int e = 0; e < EPL; e++) { a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); c = fma(x[e], y[e], c); }
       a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
       if (!(c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b))) {
         if (lane == 0) atomicAdd(rotations, 1);
@@ -113,19 +117,106 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
 #pragma unroll
         for (int e = 0; e < EPL; e++) {
           const int j = lane + 32 * e;
-          if (j < n) { gp[j] = cs * x[e] - sn * y[e]; gq[j] = sn * x[e] + cs * y[e]; }
+          if (j < n) {
+            gp[j] = cs * x[e] - sn * y[e]; gq[j] = sn * x[e] + cs * y[e];
+            jp[j] = cs * u[e] - sn * v[e]; jq[j] = sn * u[e] + cs * v[e];
+          }
         }
-        double* jp = J + (int64_t)p * n; double* jq = J + (int64_t)q * n;
+      }
+    }
+    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
+  }
+}
+
+// Block one-sided Jacobi: a CTA owns a PAIR OF ROW BLOCKS (2*BR rows of G and of J, staged in shared
+// memory) and performs all rotations between them with only block-level barriers; the grid-wide barrier
+// (the expensive part, ~5 us) is needed once per block round, i.e. BR times less often than in the
+// row-pair kernel above.  Round 0 of a sweep rotates every pair of the 2*BR local rows (this covers the
+// pairs inside a block exactly once per sweep), later rounds rotate only the BR*BR cross pairs.
+template <int BR, int EPL>
+__global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
+                                                                 double tol, int* __restrict__ rotations, unsigned* bar) {
+  extern __shared__ __align__(16) double jsm[];
+  double* Gs = jsm;                       // [2*BR][n]
+  double* Js = jsm + (size_t)2 * BR * n;  // [2*BR][n]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i = blockIdx.x;
+  for (int round = 0; round < nbe - 1; round++) {
+    int bp, bq;
+    if (i == 0) { bp = nbe - 1; bq = round; }
+    else { bp = (round + i) % (nbe - 1); bq = (round - i + (nbe - 1)) % (nbe - 1); }
+    if (bp > bq) { int tmp = bp; bp = bq; bq = tmp; }
+    // ---- stage the 2*BR rows (rows >= n are phantom: zeros, never stored)
+    for (int lr = warp; lr < 2 * BR; lr += 8) {
+      const int gr = (lr < BR ? bp * BR + lr : bq * BR + (lr - BR));
+      const bool ok = gr < n;
+      double gv[EPL], jv[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const int j = lane + 32 * e;
+        gv[e] = (ok && j < n) ? __ldcg(Gm + (int64_t)gr * n + j) : 0.0;
+        jv[e] = (ok && j < n) ? __ldcg(J + (int64_t)gr * n + j) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const int j = lane + 32 * e;
+        if (j < n) { Gs[(size_t)lr * n + j] = gv[e]; Js[(size_t)lr * n + j] = jv[e]; }
+      }
+    }
+    __syncthreads();
+    const int nmini = (round == 0) ? (2 * BR - 1) : BR;
+    for (int k = 0; k < nmini; k++) {
+      if (warp < BR) {
+        int a, b;
+        if (round == 0) {      // round-robin over the 2*BR local rows
+          const int ne2 = 2 * BR;
+          if (warp == 0) { a = ne2 - 1; b = k; }
+          else { a = (k + warp) % (ne2 - 1); b = (k - warp + (ne2 - 1)) % (ne2 - 1); }
+        } else { a = warp; b = BR + (warp + k) % BR; }
+        double* x = Gs + (size_t)a * n; double* y = Gs + (size_t)b * n;
+        double xv[EPL], yv[EPL];
+        double sa = 0, sb = 0, sc = 0;
 #pragma unroll
         for (int e = 0; e < EPL; e++) {
           const int j = lane + 32 * e;
-          x[e] = (j < n) ? __ldcg(jp + j) : 0.0;
-          y[e] = (j < n) ? __ldcg(jq + j) : 0.0;
+          xv[e] = (j < n) ? x[j] : 0.0; yv[e] = (j < n) ? y[j] : 0.0;
         }
+#pragma unroll
+        for (int e = 0; e < EPL; e++) { sa = fma(xv[e], xv[e], sa); sb = fma(yv[e], yv[e], sb); sc = fma(xv[e], yv[e], sc); }
+        sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc);
+        if (!(sc == 0.0 || fabs(sc) <= tol * sqrt(sa) * sqrt(sb))) {
+          if (lane == 0) atomicAdd(rotations, 1);
+          const double zeta = (sb - sa) / (2.0 * sc);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          double* u = Js + (size_t)a * n; double* v = Js + (size_t)b * n;
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int j = lane + 32 * e;
+            if (j < n) { x[j] = cs * xv[e] - sn * yv[e]; y[j] = sn * xv[e] + cs * yv[e]; }
+          }
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int j = lane + 32 * e;
+            xv[e] = (j < n) ? u[j] : 0.0; yv[e] = (j < n) ? v[j] : 0.0;
+          }
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int j = lane + 32 * e;
+            if (j < n) { u[j] = cs * xv[e] - sn * yv[e]; v[j] = sn * xv[e] + cs * yv[e]; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- write the rows back
+    for (int lr = warp; lr < 2 * BR; lr += 8) {
+      const int gr = (lr < BR ? bp * BR + lr : bq * BR + (lr - BR));
+      if (gr < n) {
 #pragma unroll
         for (int e = 0; e < EPL; e++) {
           const int j = lane + 32 * e;
-          if (j < n) { jp[j] = cs * x[e] - sn * y[e]; jq[j] = sn * x[e] + cs * y[e]; }
+          if (j < n) { Gm[(int64_t)gr * n + j] = Gs[(size_t)lr * n + j]; J[(int64_t)gr * n + j] = Js[(size_t)lr * n + j]; }
         }
       }
     }
@@ -190,10 +281,31 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
     void* sweep_fn = ni <= 128 ? (void*)jacobi_sweep_kernel<4> : ni <= 256 ? (void*)jacobi_sweep_kernel<8>
                    : ni <= 512 ? (void*)jacobi_sweep_kernel<16> : (void*)jacobi_sweep_kernel<32>;
     const bool use_coop = coop && ni <= 1024 && sweep_blocks <= nsm;
+    // block variant: BR rows per block, 2*BR*n*16 bytes of shared memory per CTA
+    int br = 0;
+    if (coop && ni >= 64 && !getenv("PL_JACOBI_ROWPAIR")) {
+      if ((size_t)2 * 8 * ni * 16 <= 200 * 1024) br = 8; else if (ni <= 1024 && (size_t)2 * 4 * ni * 16 <= 200 * 1024) br = 4;
+    }
+    int nbe = 0; size_t bsm = 0; void* bfn = nullptr;
+    if (br) {
+      const int nblk = (ni + br - 1) / br;
+      nbe = nblk + (nblk & 1);
+      bsm = (size_t)2 * br * ni * 16;
+      if (br == 8) bfn = ni <= 128 ? (void*)jacobi_block_sweep_kernel<8, 4> : ni <= 256 ? (void*)jacobi_block_sweep_kernel<8, 8>
+                       : ni <= 512 ? (void*)jacobi_block_sweep_kernel<8, 16> : (void*)jacobi_block_sweep_kernel<8, 25>;
+      else bfn = (void*)jacobi_block_sweep_kernel<4, 32>;
+      if (nbe / 2 > nsm) br = 0;
+      else PL_CUDA(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    }
     unsigned* bar = reinterpret_cast<unsigned*>(rot + 1);
     for (; sweeps < max_sweeps;) {
       PL_CUDA(cudaMemsetAsync(rot, 0, 2 * sizeof(int), st));
-      if (use_coop) {
+      if (br) {
+        double tol_ = tol; int ni_ = ni, nbe_ = nbe;
+        void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &rot, &bar};
+        PL_CUDA(cudaLaunchCooperativeKernel(bfn, dim3(nbe / 2), dim3(256), args, bsm, st));
+        count_launches(1);
+      } else if (use_coop) {
         double tol_ = tol; int ni_ = ni, ne_ = ne;
         void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &rot, &bar};
         PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));

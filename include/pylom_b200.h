@@ -85,6 +85,8 @@ int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S,
 /* Same signature and meaning as the reference's dtsqr_svd but HOST pointers (what a ctypes / Cython
  * binding of the reference would pass): allocates device memory, copies in, computes, copies back. */
 int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n);
+/* the host entry point keeps its device buffers between calls (grow-only); this releases them */
+void pl_host_cache_free(void);
 
 /* instrumentation: number of kernel launches issued by this library since load */
 int64_t pl_launch_count(void);

@@ -32,6 +32,7 @@ _SIGS = {
     "pl_pod_run_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
     "pl_reconstruct_f64": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "pl_tsqr_svd_host_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "pl_host_cache_free": (None, []),
     "pl_profile_enable": (None, [_int]),
     "pl_profile_read": (_int, [_vp, _vp, _int]),
 }

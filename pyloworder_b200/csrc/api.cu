@@ -29,7 +29,7 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 // ---- workspace layout for one tall matrix ---------------------------------------------------
 struct WsLayout {
   Plan plan;
-  size_t vb, tws, vup, ptmp, r, bp, ur, svd, vt, s, total;
+  size_t vb, tws, vup, vpiv, r, bp, ur, svd, vt, s, total;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static WsLayout make_layout(int64_t m, int64_t n) {
@@ -40,7 +40,7 @@ static WsLayout make_layout(int64_t m, int64_t n) {
   L.vb = off;   off += al((size_t)P.mrows * P.npad * 8);
   L.tws = off;  off += al((size_t)P.t_tiles * NB * NB * 8);
   L.vup = off;  off += al((size_t)(P.vup_tiles > 0 ? P.vup_tiles : 1) * TB * NB * 8);
-  L.ptmp = off; off += al((size_t)P.mrows * NB * 8);
+  L.vpiv = off; off += al((size_t)P.vpiv_strips * NB * NB * 8);
   L.r = off;    off += al((size_t)n * n * 8);
   const int64_t kp = round_up(n, 16), np = round_up(n, 64);
   L.bp = off;   off += al((size_t)kp * np * 8);
@@ -71,7 +71,7 @@ static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int6
     if (rc) return rc;
     PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
   }
-  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), st);
+  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
   if (rc) return rc;
   if (R) rc = caqr_extract_r(P, Vb, R, n, st);
   return rc;
@@ -83,7 +83,7 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   double* Vb = at(ws, L.vb);
   int rc;
   if (!(flags & 1)) {
-    rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.ptmp), st);
+    rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
     if (rc) return rc;
   }
   if (!W) {
@@ -227,24 +227,39 @@ int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S,
   return gemm_tall(X, n, U, ldu, (double*)ws, np, m, n, N, st);
 }
 
+// Device buffers of the host-pointer entry point are cached across calls (grow-only): a 100 GB cudaMalloc /
+// cudaFree pair per call costs several hundred milliseconds.  pl_host_cache_free() releases them.
+static struct HostCache { void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t cap[5] = {0, 0, 0, 0, 0}; } g_hc;
+static int hc_get(int slot, size_t bytes, void** out) {
+  if (g_hc.cap[slot] < bytes) {
+    if (g_hc.p[slot]) cudaFree(g_hc.p[slot]);
+    g_hc.p[slot] = nullptr; g_hc.cap[slot] = 0;
+    cudaError_t e = cudaMalloc(&g_hc.p[slot], bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return 1000 + (int)e; }
+    g_hc.cap[slot] = bytes;
+  }
+  *out = g_hc.p[slot];
+  return 0;
+}
+void pl_host_cache_free(void) {
+  for (int i = 0; i < 5; i++) { if (g_hc.p[i]) cudaFree(g_hc.p[i]); g_hc.p[i] = nullptr; g_hc.cap[i] = 0; }
+}
+
 int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
   PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
   const size_t ab = (size_t)m * n * 8, wsb = pl_qr_workspace_bytes(m, n);
-  double *dA = nullptr, *dU = nullptr, *dS = nullptr, *dV = nullptr; void* ws = nullptr;
+  void *dA = nullptr, *dU = nullptr, *dS = nullptr, *dV = nullptr, *ws = nullptr;
   cudaStream_t st = nullptr;
-  int rc = 0;
-  auto cleanup = [&]() { cudaFree(dA); cudaFree(dU); cudaFree(dS); cudaFree(dV); cudaFree(ws); };
-#define PL_H(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); cleanup(); return 1000 + (int)_e; } } while (0)
-  PL_H(cudaMalloc(&dA, ab)); PL_H(cudaMalloc(&dU, ab));
-  PL_H(cudaMalloc(&dS, (size_t)n * 8)); PL_H(cudaMalloc(&dV, (size_t)n * n * 8)); PL_H(cudaMalloc(&ws, wsb));
-  PL_H(cudaMemcpyAsync(dA, Ai, ab, cudaMemcpyHostToDevice, st));
-  rc = pl_tsqr_svd_f64(dU, dS, dV, dA, m, n, ws, wsb, st);
-  if (rc) { cleanup(); return rc; }
-  PL_H(cudaMemcpyAsync(Ui, dU, ab, cudaMemcpyDeviceToHost, st));
-  PL_H(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  PL_H(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
-  PL_H(cudaStreamSynchronize(st));
-  cleanup();
+  int rc;
+  if ((rc = hc_get(0, ab, &dA)) || (rc = hc_get(1, ab, &dU)) || (rc = hc_get(2, (size_t)n * 8, &dS)) ||
+      (rc = hc_get(3, (size_t)n * n * 8, &dV)) || (rc = hc_get(4, wsb, &ws))) { pl_host_cache_free(); return rc; }
+  PL_CUDA(cudaMemcpyAsync(dA, Ai, ab, cudaMemcpyHostToDevice, st));
+  rc = pl_tsqr_svd_f64((double*)dU, (double*)dS, (double*)dV, (const double*)dA, m, n, ws, wsb, st);
+  if (rc) return rc;
+  PL_CUDA(cudaMemcpyAsync(Ui, dU, ab, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

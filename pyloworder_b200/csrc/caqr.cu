@@ -33,7 +33,7 @@ Plan make_plan(int64_t m, int64_t n) {
   P.npad = round_up(n, NB);
   P.K = (int)(P.npad / NB);
   P.mrows = m + P.npad + NB;
-  P.t_tiles = 0; P.vup_tiles = 0;
+  P.t_tiles = 0; P.vup_tiles = 0; P.vpiv_strips = 0;
   P.panels.resize(P.K);
   for (int p = 0; p < P.K; p++) {
     int64_t m_act = m - (int64_t)p * NB;
@@ -51,7 +51,8 @@ Plan make_plan(int64_t m, int64_t n) {
       }
       L.nstrips = ceil_div(L.ntiles, L.s);
       L.t_off = P.t_tiles; P.t_tiles += L.ntiles;
-      if (li > 0) { L.v_off = P.vup_tiles; P.vup_tiles += L.ntiles; } else L.v_off = -1;
+      if (li > 0) { L.v_off = P.vup_tiles; P.vup_tiles += L.ntiles; L.p_off = -1; }
+      else { L.v_off = -1; L.p_off = P.vpiv_strips; P.vpiv_strips += L.nstrips; }
       P.panels[p].push_back(L);
       if (L.nstrips == 1) break;
       nblk = L.nstrips; bs = bs * G * L.s; li++;
@@ -109,7 +110,8 @@ extern "C" int pl_debug_panel_read(unsigned long long* out) {
 template <int MINB>
 __global__ void __launch_bounds__(160, MINB)
 caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, int64_t nblk, int64_t bs,
-                  int64_t ntiles, int s, int upper, double* __restrict__ Tl, double* __restrict__ Vupl) {
+                  int64_t ntiles, int s, int upper, double* __restrict__ Tl, double* __restrict__ Vupl,
+                  double* __restrict__ Vpivl) {
   __shared__ __align__(16) double xs[2][5][32];   // pivot column of step j (buffer j&1), pre-published during step j-1
   __shared__ double red[2][5][32];
   __shared__ double prow[2][32];
@@ -308,10 +310,10 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
 #pragma unroll
         for (int r = 0; r < 32; r++) blkp[(int64_t)r * ld] = a[r];
       }
-      if (warp == 0 && i == 0) {   // strictly-lower part of the pivot block = reflector entries
-        double* dst = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
+      if (warp == 0 && i == 0) {   // explicit unit-lower pivot-block reflectors -> side store (the in-place
+        double* dst = Vpivl + (int64_t)blockIdx.x * (NB * NB) + lane;   // rows are reused when Q is formed)
 #pragma unroll 8
-        for (int r = 1; r < 32; r++) if (r > lane) dst[(int64_t)r * ld] = Rs[r][lane];
+        for (int r = 0; r < 32; r++) dst[r * NB] = (r > lane) ? Rs[r][lane] : ((r == lane) ? 1.0 : 0.0);
       }
     } else {
       double* Vt = Vupl + t * (TB * NB);
@@ -356,7 +358,7 @@ struct UpdSmem {
 struct UpdArgs {
   const double* Vb; int64_t ld; int64_t row0; int col0;
   int64_t nblk, bs, ntiles; int s; int upper; int forward;
-  const double* Tl; const double* Vupl;
+  const double* Tl; const double* Vupl; const double* Vpivl; int virt;
   double* C0; int64_t ldc0; int coff0; int nchunk0;
   double* C1; int64_t ldc1; int coff1;
 };
@@ -410,13 +412,19 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
         const double* vs = valid ? (vp + q * v_q) : vp;
         const double* cs = valid ? (cp + q * c_q) : cp;
         const bool vok = valid || upper;
-        cp_async16(&S.Vs[q][r_lo][c2], vs, vok);
-        cp_async16(&S.Vs[q][r_lo + 16][c2], vs + v_h, vok);
+        if (q == 0 && first && !upper) {   // explicit unit-lower pivot block of a level-0 strip
+          const double* ps = A.Vpivl + (int64_t)blockIdx.y * (NB * NB) + r_lo * NB + c2;
+          cp_async16(&S.Vs[0][r_lo][c2], ps, true);
+          cp_async16(&S.Vs[0][r_lo + 16][c2], ps + 16 * NB, true);
+        } else {
+          cp_async16(&S.Vs[q][r_lo][c2], vs, vok);
+          cp_async16(&S.Vs[q][r_lo + 16][c2], vs + v_h, vok);
+        }
         if (q == 0 && first) {
           if (A.forward) { cp_async16(&S.Zs[r_lo][c2], cs, true); cp_async16(&S.Zs[r_lo + 16][c2], cs + c_h, true); }
         } else {
-          cp_async16(&S.Cs[q][r_lo][c2], cs, valid);
-          cp_async16(&S.Cs[q][r_lo + 16][c2], cs + c_h, valid);
+          cp_async16(&S.Cs[q][r_lo][c2], cs, valid && !A.virt);   // virt: the block is known to be zero
+          cp_async16(&S.Cs[q][r_lo + 16][c2], cs + c_h, valid && !A.virt);
         }
       }
       const double* tp = tbase + t * (NB * NB);
@@ -426,13 +434,6 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (first && !upper) {   // explicit unit-lower pivot block from the in-place storage
-      for (int e = tid; e < NB * NB; e += 256) {
-        int r = e >> 5, c = e & 31;
-        if (c > r) S.Vs[0][r][c] = 0.0; else if (c == r) S.Vs[0][r][c] = 1.0;
-      }
-      __syncthreads();
-    }
     const double (*C0)[SP] = first ? S.Zs : S.Cs[0];   // slab 0 of the first tile is the carried block
 
     // ---- GEMM1: W = V^T C (+ Z)      two independent accumulator chains (even / odd k16 steps)
@@ -555,34 +556,19 @@ __global__ void zero_r_right_kernel(double* Vb, int64_t ld, int npad) {
   int r = (int)(idx / npad), c = (int)(idx % npad);
   if (c >= (r / NB + 1) * NB) Vb[(int64_t)r * ld + c] = 0.0;
 }
-// Ptmp rows [row0, mrows): zero, identity block at row0
-__global__ void ptmp_init_kernel(double* Ptmp, int64_t row0, int64_t mrows) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // double2 index
-  int64_t tot = (mrows - row0) * (NB / 2);
-  for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = idx / (NB / 2); int c = (int)(idx % (NB / 2)) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (r < NB) { if (c == r) v.x = 1.0; if (c + 1 == r) v.y = 1.0; }
-    reinterpret_cast<double2*>(Ptmp + (row0 + r) * NB)[c >> 1] = v;
-  }
-}
-// Vb[:, col0:col0+NB] <- Ptmp (rows >= row0), 0 (rows < row0)
-__global__ void ptmp_copyback_kernel(double* Vb, int64_t ld, int col0, const double* Ptmp, int64_t row0, int64_t mrows) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t tot = mrows * (NB / 2);
-  for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = idx / (NB / 2); int c = (int)(idx % (NB / 2)) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (r >= row0) v = reinterpret_cast<const double2*>(Ptmp + r * NB)[c >> 1];
-    *reinterpret_cast<double2*>(Vb + r * ld + col0 + c) = v;
-  }
+// Vb[row0:row0+NB, col0:col0+NB] <- I   (input of the panel's own columns when Q is formed)
+__global__ void set_identity_block_kernel(double* Vb, int64_t ld, int64_t row0, int col0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NB * NB) return;
+  const int r = e >> 5, c = e & 31;
+  Vb[(row0 + r) * ld + col0 + c] = (r == c) ? 1.0 : 0.0;
 }
 
 // =============================================================================================
 // drivers
 // =============================================================================================
 static int launch_update(const Plan& P, int p, const Level& L, int li, const double* Vb, const double* Tws,
-                         const double* Vup, double* C0, int64_t ldc0, int coff0, int nchunk0, double* C1, int64_t ldc1,
+                         const double* Vup, const double* Vpiv, int virt, double* C0, int64_t ldc0, int coff0, int nchunk0, double* C1, int64_t ldc1,
                          int coff1, int nchunk1, int forward, cudaStream_t st) {
   if (nchunk0 + nchunk1 <= 0) return 0;
   UpdArgs A;
@@ -590,6 +576,8 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   A.nblk = L.nblk; A.bs = L.bs; A.ntiles = L.ntiles; A.s = L.s; A.upper = li > 0; A.forward = forward;
   A.Tl = Tws + L.t_off * (NB * NB);
   A.Vupl = (li > 0) ? (Vup + L.v_off * (TB * NB)) : nullptr;
+  A.Vpivl = (li > 0) ? nullptr : (Vpiv + L.p_off * (NB * NB));
+  A.virt = virt;
   A.C0 = C0; A.ldc0 = ldc0; A.coff0 = coff0; A.nchunk0 = nchunk0;
   A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1;
   static bool attr_set = false;
@@ -608,6 +596,7 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
     B.ntiles = L.ntiles - done * L.s;
     B.Tl = A.Tl + done * L.s * (NB * NB);
     if (B.Vupl) B.Vupl = A.Vupl + done * L.s * (TB * NB);
+    if (B.Vpivl) B.Vpivl = A.Vpivl + done * (NB * NB);
     dim3 grid((unsigned)(nchunk0 + nchunk1), (unsigned)ny);
     {
       ProfScope ps(forward ? PROF_UPDATE_F : PROF_UPDATE_Q, st);
@@ -619,7 +608,7 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   return 0;
 }
 
-int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_t st) {
+int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st) {
   for (int p = 0; p < P.K; p++) {
     const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
@@ -631,18 +620,21 @@ int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_
         if (occ == 4)
           caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
                                                                   li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
+                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
         else if (occ == 2)
           caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
                                                                   li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
+                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
         else
           caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
                                                                   li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr);
+                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
+                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
       }
       PL_LAUNCH_CHECK();
-      int rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
+      int rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
       if (rc) return rc;
     }
   }
@@ -657,30 +649,34 @@ int caqr_extract_r(const Plan& P, const double* Vb, double* R, int64_t ldr, cuda
 }
 
 // Overwrite the reflectors in Vb with the explicit thin Q (rows < m, columns < n are meaningful).
-int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, double* Ptmp, cudaStream_t st) {
+// dorgqr-style backward accumulation: for panel p = K-1 .. 0 the block reflectors are applied (levels top
+// down, tiles in reverse order) to the trailing columns, then to the panel's own columns, whose input is
+// the identity block on the panel's pivot rows and (virtually) zero elsewhere; the result overwrites the
+// reflectors in place -- the pivot-block reflectors needed afterwards live in the Vpiv side store.
+int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, const double* Vpiv, cudaStream_t st) {
   {
     int64_t tot = P.npad * P.npad;
+    ProfScope ps(PROF_MISC, st);
     zero_r_right_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(Vb, P.npad, (int)P.npad);
     PL_LAUNCH_CHECK();
   }
   for (int p = P.K - 1; p >= 0; p--) {
     const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
-    {
-      ProfScope ps(PROF_MISC, st);
-      ptmp_init_kernel<<<148 * 8, 256, 0, st>>>(Ptmp, row0, P.mrows);
-    }
-    PL_LAUNCH_CHECK();
-    for (int li = (int)P.panels[p].size() - 1; li >= 0; li--) {
-      const Level& L = P.panels[p][li];
-      int rc = launch_update(P, p, L, li, Vb, Tws, Vup, Ptmp, NB, 0, 1, Vb, P.npad, col0 + NB, ntrail, 0, st);
+    const int nl = (int)P.panels[p].size();
+    for (int li = nl - 1; li >= 0; li--) {
+      int rc = launch_update(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 0, st);
       if (rc) return rc;
     }
     {
       ProfScope ps(PROF_MISC, st);
-      ptmp_copyback_kernel<<<148 * 8, 256, 0, st>>>(Vb, P.npad, col0, Ptmp, row0, P.mrows);
+      set_identity_block_kernel<<<4, 256, 0, st>>>(Vb, P.npad, row0, col0);
+      PL_LAUNCH_CHECK();
     }
-    PL_LAUNCH_CHECK();
+    for (int li = nl - 1; li >= 0; li--) {
+      int rc = launch_update(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, 1, Vb, P.npad, col0, 1, nullptr, 0, 0, 0, 0, st);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

@@ -14,19 +14,20 @@ struct Level {
   int64_t nstrips;
   int64_t t_off;    // tile offset of this level in the T store
   int64_t v_off;    // tile offset in the upper-level reflector store (-1 at level 0: in place)
+  int64_t p_off;    // strip offset in the pivot-block reflector store (level 0 only, else -1)
 };
 
 struct Plan {
   int64_t m, n, npad, mrows;
   int K;                                   // panels
   std::vector<std::vector<Level>> panels;  // [panel][level]
-  int64_t t_tiles, vup_tiles;              // totals
+  int64_t t_tiles, vup_tiles, vpiv_strips; // totals
 };
 
 Plan make_plan(int64_t m, int64_t n);
-int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, cudaStream_t st);
+int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st);
 int caqr_extract_r(const Plan& P, const double* Vb, double* R, int64_t ldr, cudaStream_t st);
-int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, double* Ptmp, cudaStream_t st);
+int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, const double* Vpiv, cudaStream_t st);
 
 // center.cu
 int temporal_mean(double* out, const double* X, int64_t m, int64_t n, cudaStream_t st);

@@ -243,15 +243,24 @@ __global__ void rank_kernel(int* rank, const double* s, int n) {
   }
 }
 
+// Row k of G is sigma_k * (right singular vector), row k of J is the left singular vector.  Ten million
+// slightly non-orthogonal rotations (n ~ 1000, 20 sweeps) let the norms of the rows of J random-walk by
+// ~1e-12, mostly on the modes with tiny sigma; the rows stay mutually orthogonal to ~1e-14, so they are
+// renormalised here (the classical Jacobi-SVD clean-up, cf. the normalisation of the columns of U in xGESVJ).
 __global__ void __launch_bounds__(128) svd_scatter_kernel(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt,
                                                           const double* Gm, const double* J, const double* s,
                                                           const int* rank, int n) {
+  __shared__ double sh[3][4];
   const int k = blockIdx.x, r = rank[k];
   const double sk = s[k], inv = sk > 0.0 ? 1.0 / sk : 0.0;
+  double a = 0, b = 0, c = 0;
+  for (int j = threadIdx.x; j < n; j += 128) { const double x = J[(int64_t)k * n + j]; a += x * x; }
+  block_sum3(a, b, c, sh);
+  const double jinv = a > 0.0 ? 1.0 / sqrt(a) : 0.0;
   if (threadIdx.x == 0) S[r] = sk;
   for (int j = threadIdx.x; j < n; j += 128) {
     VT[(int64_t)r * ldvt + j] = Gm[(int64_t)k * n + j] * inv;
-    Ur[(int64_t)j * ldu + r] = J[(int64_t)k * n + j];
+    Ur[(int64_t)j * ldu + r] = J[(int64_t)k * n + j] * jinv;
   }
 }
 

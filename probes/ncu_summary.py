@@ -1,0 +1,23 @@
+"""Summarise an ncu report (raw page) into a few lines for profiles/."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h = rows[0]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+for r in rows[2:]:
+    print("=" * 100)
+    for w in want:
+        if w in h:
+            print(f"{w:90s} {r[h.index(w)]:>20s} {rows[1][h.index(w)]}")
+    st = {n.replace("smsp__pcsamp_warps_issue_stalled_", ""): int(float(r[i] or 0)) for i, n in enumerate(h)
+          if n.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in n}
+    tot = sum(st.values()) or 1
+    print("stall samples (%):", ", ".join(f"{k} {100 * v / tot:.1f}" for k, v in sorted(st.items(), key=lambda x: -x[1])[:10]))

@@ -32,6 +32,12 @@ int pl_subtract_mean_f64(double* out, const double* X, const double* X_mean, int
 /* fused temporal_mean + subtract_mean (what POD.run does back to back, POD/wrapper.pyx:127-133) */
 int pl_center_f64(double* Y, double* X_mean, const double* X, int64_t m, int64_t n, void* stream);
 
+/* replaces dtemporal_variance(double *out, double *X, double *Xmean, m, n): population variance  averaging.c:70-90 */
+int pl_temporal_variance_f64(double* out, const double* X, const double* X_mean, int64_t m, int64_t n, void* stream);
+/* replaces dsubtract_mean + dnorm_variance (averaging.c:143-158): out = (X - X_mean) / X_var, the body of
+ * norm_variance(X, X_mean, X_var) in pyLOM/vmmath/averaging.py:61-74 */
+int pl_norm_variance_f64(double* out, const double* X, const double* X_mean, const double* X_var, int64_t m, int64_t n, void* stream);
+
 /* ---- dense helpers:  pyLOM/vmmath/src/vector_matrix.h ---------------------------------------- */
 /* replaces dmatmul(double *C, double *A, double *B, m, n, k): C(m,n) = A(m,k) B(k,n)  vector_matrix.c:234-242.
  * lda/ldc allow the strided views POD.truncate returns (POD/wrapper.py:78-80). */
@@ -56,6 +62,10 @@ size_t pl_qr_workspace_bytes(int64_t m, int64_t n);
  * the diagonal, svd.c:304-307).  A is not modified.  X_mean (m) may be NULL when center == 0. */
 int pl_qr_factor_f64(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center,
                      void* ws, size_t ws_bytes, void* stream);
+/* Same with the POD.run(divide_variance=True) preprocessing fused in: the factored matrix is
+ * (A - rowmean) / rowvariance (POD/wrapper.py:36-38); X_mean and X_var (m each) are outputs. */
+int pl_qr_factor_var_f64(double* R, double* X_mean, double* X_var, const double* A, int64_t m, int64_t n,
+                         void* ws, size_t ws_bytes, void* stream);
 /* Second half of dqr (LAPACKE_dorgqr) fused with the back-multiplies of dtsqr/dtsqr_svd
  * (dmatmul at svd.c:673 and svd.c:708):  U(m, nw) = Q1 * W, W (n x nw, ldw) on the device.
  * W == NULL gives U = Q1 (nw must equal n).  Must follow pl_qr_factor_f64 on the same workspace.

@@ -62,6 +62,16 @@ def subtract_mean(X: np.ndarray, X_mean: np.ndarray) -> np.ndarray:
     return X - X_mean[:, None]
 
 
+def temporal_variance(X: np.ndarray, X_mean: np.ndarray) -> np.ndarray:
+    """Population variance per row, keepdims (pyLOM/vmmath/averaging.py:46-59, src/averaging.c:70-90)."""
+    return np.var(X, axis=1, keepdims=True)
+
+
+def norm_variance(X, X_mean, X_var):
+    """(X - X_mean)/X_var (pyLOM/vmmath/averaging.py:61-74)."""
+    return subtract_mean(X, X_mean) / X_var
+
+
 # --------------------------------------------------------------------------------------
 # small dense algebra
 # --------------------------------------------------------------------------------------
@@ -182,12 +192,14 @@ def tsqr_svd(A_list):
 # --------------------------------------------------------------------------------------
 # POD
 # --------------------------------------------------------------------------------------
-def pod_run(X_list, remove_mean: bool = True):
+def pod_run(X_list, remove_mean: bool = True, divide_variance: bool = False):
     """POD.run on P simulated ranks (pyLOM/POD/wrapper.py:16-51).  ``X_list`` may be a
-    single array.  divide_variance / randomized are outside the hot path."""
+    single array.  randomized is outside the hot path."""
     single = isinstance(X_list, np.ndarray)
     Xs = [X_list] if single else X_list
-    if remove_mean:
+    if remove_mean and divide_variance:
+        Ys = [norm_variance(X, temporal_mean(X), temporal_variance(X, temporal_mean(X))) for X in Xs]
+    elif remove_mean:
         Ys = [subtract_mean(X, temporal_mean(X)) for X in Xs]
     else:
         Ys = [X.copy() for X in Xs]

@@ -6,6 +6,7 @@ from .. import _lib, _dev
 from ..utils.cr import cr, cr_start, cr_stop
 from ..vmmath.svd import _tsqr_svd_dev
 from ..vmmath.truncation import compute_truncation_residual
+from ..vmmath.averaging import temporal_mean, temporal_variance, norm_variance
 
 
 @cr('POD.run')
@@ -14,16 +15,21 @@ def run(X, remove_mean=True, divide_variance=False, randomized=False, r=1, q=3, 
 
     Returns U (m_i, n) spatial modes, S (n) singular values, V (n, n) = V^T temporal coefficients.
     X is not modified.  The centering (temporal_mean + subtract_mean, POD/wrapper.py:33-41) is fused
-    into the copy that feeds the factorisation.  `divide_variance` and `randomized` are outside the
-    B200 hot path and raise NotImplementedError.
+    into the copy that feeds the factorisation.  `randomized` is outside the B200 hot path
+     and raises NotImplementedError.
     """
-    if divide_variance:
-        raise NotImplementedError("POD.run(divide_variance=True) is not part of the B200 hot path yet")
     if randomized:
         raise NotImplementedError("POD.run(randomized=True) is not part of the B200 hot path yet")
     Xd, kind = _dev.to_device(X, "X")
+    center = bool(remove_mean)
+    if remove_mean and divide_variance:      # POD/wrapper.py:36-38 (only effective together with remove_mean)
+        cr_start('POD.temporal_mean', 0)
+        X_mean = temporal_mean(Xd)
+        Xd = norm_variance(Xd, X_mean, temporal_variance(Xd, X_mean))
+        cr_stop('POD.temporal_mean', 0)
+        center = False
     cr_start('POD.SVD', 0)
-    U, S, V, _ = _tsqr_svd_dev(Xd, center=bool(remove_mean))
+    U, S, V, _ = _tsqr_svd_dev(Xd, center=center)
     cr_stop('POD.SVD', 0)
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(V, kind)
 

@@ -18,6 +18,9 @@ _SIGS = {
     "pl_temporal_mean_f64": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "pl_subtract_mean_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pl_center_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "pl_temporal_variance_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "pl_norm_variance_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "pl_qr_factor_var_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
     "pl_matmul_workspace_bytes": (_sz, [_i64, _i64]),
     "pl_matmul_f64": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "pl_vecmat_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),

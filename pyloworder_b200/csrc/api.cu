@@ -60,13 +60,14 @@ static int check_ws(const WsLayout& L, void* ws, size_t ws_bytes, int argpos) {
 }
 
 static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center, void* ws,
-                     const WsLayout& L, cudaStream_t st) {
+                     const WsLayout& L, cudaStream_t st, double* X_var = nullptr) {
   const Plan& P = L.plan;
   double* Vb = at(ws, L.vb);
   int rc;
   {
     ProfScope ps(PROF_COPY, st);
-    if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
+    if (center == 2) rc = center_var_rows(Vb, P.npad, X_mean, X_var, A, m, n, P.npad, st);
+    else if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
     else rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
     if (rc) return rc;
     PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
@@ -134,6 +135,14 @@ int pl_center_f64(double* Y, double* X_mean, const double* X, int64_t m, int64_t
   PL_ARG(m >= 0 && n > 0, 4, "m >= 0, n > 0");
   return center_rows(Y, n, X_mean, X, m, n, n, (cudaStream_t)stream);
 }
+int pl_temporal_variance_f64(double* out, const double* X, const double* X_mean, int64_t m, int64_t n, void* stream) {
+  PL_ARG(m >= 0 && n > 0, 4, "m >= 0, n > 0");
+  return temporal_variance(out, X, X_mean, m, n, (cudaStream_t)stream);
+}
+int pl_norm_variance_f64(double* out, const double* X, const double* X_mean, const double* X_var, int64_t m, int64_t n, void* stream) {
+  PL_ARG(m >= 0 && n > 0, 5, "m >= 0, n > 0");
+  return norm_variance(out, n, X, X_mean, X_var, m, n, n, (cudaStream_t)stream);
+}
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream) {
   return vecmat(C, n, v, A, n, m, n, (cudaStream_t)stream);
 }
@@ -168,6 +177,16 @@ int pl_qr_factor_f64(double* R, double* X_mean, const double* A, int64_t m, int6
   int rc = check_ws(L, ws, ws_bytes, 7);
   if (rc) return rc;
   return qr_factor(R, X_mean, A, m, n, center, ws, L, (cudaStream_t)stream);
+}
+
+int pl_qr_factor_var_f64(double* R, double* X_mean, double* X_var, const double* A, int64_t m, int64_t n, void* ws,
+                         size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
+  PL_ARG(X_mean && X_var, 2, "X_mean and X_var required");
+  WsLayout L = make_layout(m, n);
+  int rc = check_ws(L, ws, ws_bytes, 7);
+  if (rc) return rc;
+  return qr_factor(R, X_mean, A, m, n, 2, ws, L, (cudaStream_t)stream, X_var);
 }
 
 int pl_qr_apply_q_f64(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n, int flags,

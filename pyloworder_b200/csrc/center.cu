@@ -9,14 +9,15 @@
 
 namespace pl {
 
-enum RowMode { ROW_MEAN = 0, ROW_SUB = 1, ROW_CENTER = 2, ROW_COPY = 3 };
+enum RowMode { ROW_MEAN = 0, ROW_SUB = 1, ROW_CENTER = 2, ROW_COPY = 3, ROW_VAR = 4, ROW_NORMVAR = 5, ROW_CENTERVAR = 6 };
 
 // One group of GS lanes per row (GS = 32 for n >= 32, smaller powers of two for short rows).
 // The row is read twice in ROW_CENTER; the second read hits L1/L2 (a row is <= 8 KiB).
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) row_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src,
                                                   int64_t lds, double* __restrict__ mean_out,
-                                                  const double* __restrict__ mean_in, int64_t m, int n, int gs,
+                                                  const double* __restrict__ mean_in, double* __restrict__ var_out,
+                                                  const double* __restrict__ var_in, int64_t m, int n, int gs,
                                                   int pad_to) {
   const int lane = threadIdx.x & 31;
   const int sub = lane % gs;                 // lane inside the row group
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(256) row_kernel(double* __restrict__ dst, int6
     const bool live = row < m;
     const double* x = src + (live ? row : 0) * lds;
     double mu = 0.0;
-    if (MODE == ROW_MEAN || MODE == ROW_CENTER) {
+    double scl = 1.0;   // divisor applied after centering (the row variance in the variance-normalising modes)
+    if (MODE == ROW_MEAN || MODE == ROW_CENTER || MODE == ROW_CENTERVAR) {
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
       if (live) {
         if (VEC) {
@@ -54,10 +56,25 @@ __global__ void __launch_bounds__(256) row_kernel(double* __restrict__ dst, int6
       for (int o = gs >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       mu = s * inv_n;
       if (live && sub == 0 && mean_out) mean_out[row] = mu;
-    } else if (MODE == ROW_SUB) {
+    } else if (MODE == ROW_SUB || MODE == ROW_VAR || MODE == ROW_NORMVAR) {
       if (live) mu = mean_in[row];
     }
-    if (MODE != ROW_MEAN && live) {
+    if (MODE == ROW_VAR || MODE == ROW_CENTERVAR) {   // population variance (1/n), src/averaging.c:70-90
+      double v0 = 0, v1 = 0;
+      if (live) {
+        int j = sub;
+        for (; j + gs < n; j += 2 * gs) { double a = x[j] - mu, b = x[j + gs] - mu; v0 += a * a; v1 += b * b; }
+        for (; j < n; j += gs) { double a = x[j] - mu; v0 += a * a; }
+      }
+      double v = v0 + v1;
+      for (int o = gs >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      v *= inv_n;
+      if (live && sub == 0 && var_out) var_out[row] = v;
+      scl = v;
+    } else if (MODE == ROW_NORMVAR) {
+      if (live) scl = var_in[row];
+    }
+    if (MODE != ROW_MEAN && MODE != ROW_VAR && live) {
       double* y = dst + row * ldd;
       if (VEC) {
         const double2* xv = reinterpret_cast<const double2*>(x);
@@ -66,11 +83,12 @@ __global__ void __launch_bounds__(256) row_kernel(double* __restrict__ dst, int6
         for (int j = sub; j < nv; j += gs) {
           double2 a = xv[j];
           a.x -= mu; a.y -= mu;
+          if (MODE == ROW_NORMVAR || MODE == ROW_CENTERVAR) { a.x /= scl; a.y /= scl; }
           yv[j] = a;
         }
         for (int j = nv + sub; j < (pad_to >> 1); j += gs) yv[j] = make_double2(0.0, 0.0);
       } else {
-        for (int j = sub; j < n; j += gs) y[j] = x[j] - mu;
+        for (int j = sub; j < n; j += gs) y[j] = (MODE == ROW_NORMVAR || MODE == ROW_CENTERVAR) ? (x[j] - mu) / scl : (x[j] - mu);
         for (int j = n + sub; j < pad_to; j += gs) y[j] = 0.0;
       }
     }
@@ -88,18 +106,19 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <int MODE>
 static int launch_row(double* dst, int64_t ldd, const double* src, int64_t lds, double* mean_out,
-                      const double* mean_in, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st) {
+                      const double* mean_in, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st,
+                      double* var_out = nullptr, const double* var_in = nullptr) {
   if (m <= 0 || n <= 0) return 0;
   bool vec = (n % 2 == 0) && (lds % 2 == 0) && aligned16(src) &&
-             (MODE == ROW_MEAN || ((ldd % 2 == 0) && aligned16(dst) && (pad_to % 2 == 0)));
+             (MODE == ROW_MEAN || MODE == ROW_VAR || ((ldd % 2 == 0) && aligned16(dst) && (pad_to % 2 == 0)));
   int gs = pick_gs(n, vec);
   int64_t rows_per_block = 8 * (32 / gs);
   int64_t blocks = ceil_div(m, rows_per_block);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (vec)
-    row_kernel<MODE, true><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, m, (int)n, gs, (int)pad_to);
+    row_kernel<MODE, true><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, var_out, var_in, m, (int)n, gs, (int)pad_to);
   else
-    row_kernel<MODE, false><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, m, (int)n, gs, (int)pad_to);
+    row_kernel<MODE, false><<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, mean_out, mean_in, var_out, var_in, m, (int)n, gs, (int)pad_to);
   PL_LAUNCH_CHECK();
   return 0;
 }
@@ -114,6 +133,17 @@ int subtract_mean(double* out, int64_t ldo, const double* X, const double* mean,
 int center_rows(double* Y, int64_t ldy, double* mean, const double* X, int64_t m, int64_t n, int64_t pad_to,
                 cudaStream_t st) {
   return launch_row<ROW_CENTER>(Y, ldy, X, n, mean, nullptr, m, n, pad_to, st);
+}
+int temporal_variance(double* out, const double* X, const double* mean, int64_t m, int64_t n, cudaStream_t st) {
+  return launch_row<ROW_VAR>(nullptr, 0, X, n, nullptr, mean, m, n, n, st, out, nullptr);
+}
+int norm_variance(double* out, int64_t ldo, const double* X, const double* mean, const double* var, int64_t m, int64_t n,
+                  int64_t pad_to, cudaStream_t st) {
+  return launch_row<ROW_NORMVAR>(out, ldo, X, n, nullptr, mean, m, n, pad_to, st, nullptr, var);
+}
+int center_var_rows(double* Y, int64_t ldy, double* mean, double* var, const double* X, int64_t m, int64_t n, int64_t pad_to,
+                    cudaStream_t st) {
+  return launch_row<ROW_CENTERVAR>(Y, ldy, X, n, mean, nullptr, m, n, pad_to, st, var, nullptr);
 }
 int copy_pad(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m, int64_t n, int64_t pad_to,
              cudaStream_t st) {

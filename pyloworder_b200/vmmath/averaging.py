@@ -29,6 +29,32 @@ def subtract_mean(X, X_mean):
     return _dev.from_device(out, kind)
 
 
+@cr('math.temporal_variance')
+def temporal_variance(X, X_mean):
+    """Population variance of every row, shape (m, 1) like `p.var(X, axis=1, keepdims=True)`
+    (pyLOM/vmmath/averaging.py:46-59, src/averaging.c:70-90)."""
+    Xd, kind = _dev.to_device(X, "X")
+    Md, _ = _dev.to_device(X_mean, "X_mean")
+    m, n = Xd.shape
+    out = torch.empty(m, dtype=torch.float64, device=Xd.device)
+    _lib.check(_lib.lib().pl_temporal_variance_f64(out.data_ptr(), Xd.data_ptr(), Md.reshape(-1).data_ptr(), m, n, _dev.stream()),
+               "temporal_variance")
+    return _dev.from_device(out.reshape(m, 1), kind)
+
+
+@cr('math.temporal_variance')
+def norm_variance(X, X_mean, X_var):
+    """(X - X_mean) / X_var  (pyLOM/vmmath/averaging.py:61-74, src/averaging.c:109-158)."""
+    Xd, kind = _dev.to_device(X, "X")
+    Md, _ = _dev.to_device(X_mean, "X_mean")
+    Vd, _ = _dev.to_device(X_var, "X_var")
+    m, n = Xd.shape
+    out = torch.empty_like(Xd)
+    _lib.check(_lib.lib().pl_norm_variance_f64(out.data_ptr(), Xd.data_ptr(), Md.reshape(-1).data_ptr(),
+                                              Vd.reshape(-1).data_ptr(), m, n, _dev.stream()), "norm_variance")
+    return _dev.from_device(out, kind)
+
+
 def center(X):
     """Fused temporal_mean + subtract_mean: returns (Y, X_mean).  Not in the reference API; it is what
     POD.run does back to back (POD/wrapper.py:33-41)."""

@@ -142,6 +142,30 @@ def test_averaging_kernels(pl):
         assert np.abs(host(Z) - X).max() <= 2e-16 * np.abs(X).max() * 2
 
 
+def test_variance_normalisation(pl):
+    X = synth.snapshots(5000, 33, 8)
+    mean = po.temporal_mean(X)
+    var = pl.math.temporal_variance(dev(X), dev(mean))
+    assert var.shape == (5000, 1)
+    assert np.abs(host(var) - po.temporal_variance(X, mean)).max() <= 1e-14 * np.abs(po.temporal_variance(X, mean)).max()
+    Y = pl.math.norm_variance(dev(X), dev(mean), dev(po.temporal_variance(X, mean)))
+    assert np.array_equal(host(Y), po.norm_variance(X, mean, po.temporal_variance(X, mean)))
+    U, S, V = pl.POD.run(dev(X), remove_mean=True, divide_variance=True)
+    Uo, So, Vo = po.pod_run(X, remove_mean=True, divide_variance=True)
+    assert_svd_parity((Uo, So, Vo), (host(U), host(S), host(V)))
+    # fused C entry point (centering + variance normalisation inside the factorisation copy)
+    from pyloworder_b200 import _lib, _dev
+    L = _lib.lib()
+    m, n = X.shape
+    Xd = dev(X)
+    R = torch.empty((n, n), dtype=torch.float64, device="cuda"); mu = torch.empty(m, dtype=torch.float64, device="cuda"); vv = torch.empty_like(mu)
+    _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), "t", Xd.device)
+    assert L.pl_qr_factor_var_f64(R.data_ptr(), mu.data_ptr(), vv.data_ptr(), Xd.data_ptr(), m, n, wp, wb, None) == 0
+    Rr = np.linalg.qr(po.norm_variance(X, mean, po.temporal_variance(X, mean)), mode="r")
+    assert np.abs(np.abs(host(R)) - np.abs(Rr)).max() <= 1e-11 * np.abs(Rr).max()
+    assert np.abs(host(vv) - po.temporal_variance(X, mean)[:, 0]).max() <= 1e-14 * host(vv).max()
+
+
 def test_matmul_vecmat_reconstruct(pl):
     rng = np.random.default_rng(0)
     for m, n, k in ((1000, 64, 64), (777, 151, 151), (5000, 512, 512), (300, 40, 7), (129, 33, 100), (1, 1, 1), (257, 999, 999)):
@@ -232,3 +256,16 @@ def test_native_library_is_the_one_running(pl):
     assert _lib.lib().pl_launch_count() > before
     maps = open("/proc/self/maps").read()
     assert "libpylom_b200.so" in maps
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_nccl_parity():
+    """One process per GPU over NCCL (tests/dist_check.py): tsqr_svd / POD.run vs the oracle on the same shards."""
+    import socket, subprocess, sys
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    script = os.path.join(os.path.dirname(__file__), "dist_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

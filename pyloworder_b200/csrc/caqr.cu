@@ -43,11 +43,15 @@ Plan make_plan(int64_t m, int64_t n) {
       Level L;
       L.nblk = nblk; L.bs = bs;
       L.ntiles = ceil_div(nblk, G);
+      // tiles per strip: long strips (fewer, cheaper upper levels) while >= ~4 strips per SM remain
+      static const int smax = getenv("PL_SMAX") ? atoi(getenv("PL_SMAX")) : SMAX;
+      static const int starget = getenv("PL_STRIPS") ? atoi(getenv("PL_STRIPS")) : 592;
+      static const int ssmall = getenv("PL_SSMALL") ? atoi(getenv("PL_SSMALL")) : 2;
       if (L.ntiles > 148) {
-        int64_t s = L.ntiles / 592;
-        L.s = (int)(s < 1 ? 1 : (s > SMAX ? SMAX : s));
+        int64_t s = L.ntiles / starget;
+        L.s = (int)(s < 1 ? 1 : (s > smax ? smax : s));
       } else {
-        L.s = (int)(L.ntiles < 4 ? L.ntiles : 4);
+        L.s = (int)(L.ntiles < ssmall ? L.ntiles : ssmall);
       }
       L.nstrips = ceil_div(L.ntiles, L.s);
       L.t_off = P.t_tiles; P.t_tiles += L.ntiles;

@@ -10,7 +10,7 @@ namespace pl {
 constexpr int NB = 32;        // panel width (columns per block reflector)
 constexpr int G  = 4;         // NB-row blocks per tile
 constexpr int TB = NB * G;    // tile rows (128)
-constexpr int SMAX = 8;       // max tiles per strip (flat tree inside one CTA)
+constexpr int SMAX = 16;      // max tiles per strip (flat tree inside one CTA)
 
 // ---- error reporting (C ABI returns int, message via pl_last_error) ----------------------
 void set_error(const char* fmt, ...);

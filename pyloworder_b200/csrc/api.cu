@@ -97,7 +97,9 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   rc = pad_small(Bp, kp, np, W, ldw, n, nw, nullptr, st);
   if (rc) return rc;
   ProfScope ps(PROF_GEMM, st);
-  return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, n, st);
+  // k is rounded up to the packed height: the extra columns of Q1 (finite padding) meet zero rows of Bp,
+  // and an even k keeps the 16-byte cp.async path for odd n
+  return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, kp, st);
 }
 }  // namespace pl
 

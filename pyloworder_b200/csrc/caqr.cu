@@ -69,15 +69,16 @@ Plan make_plan(int64_t m, int64_t n) {
 // panel kernel
 // =============================================================================================
 // 160 threads = 5 warps; each warp owns one NB x NB block of the stacked [Rp; tile] matrix
-// (warp 0: the pivot block Rp, warps 1..4: the four body blocks of the tile).  In the body warps
-// LANE k HOLDS COLUMN k of the block in registers (a[r], r = row inside the block); the pivot block
-// lives in shared memory (Rs) because it needs row access (the pivot row) as well.  With this layout
-//   * the column inner products x^T P_k of a Householder step are lane-local FMA chains (no shuffle
-//     reductions); the pivot column x is published once per step through shared memory and read
-//     back with broadcast 128-bit loads;
-//   * the same 32 lane-local products deliver the norm (lane j), the trailing update (lanes > j)
-//     and the compact-WY T-factor products (lanes < j);
-//   * global loads/stores of a block row are 256 contiguous bytes per warp;
+// (warp 0: the pivot block Rp, warps 1..4: the four body blocks of the tile).  In the body warps lane
+// (cg, rg) HOLDS 4 COLUMNS x 8 ROWS of the block in registers (columns cg+8i, rows 8rg..8rg+7); the
+// pivot block lives in shared memory (Rs) because it needs row access (the pivot row) as well.  With
+// this layout
+//   * a lane needs only the 8 entries of the pivot column x that belong to its rows (4 quarter-warp
+//     broadcast loads per step instead of 32 -- the first column-per-lane version was bound by the
+//     shared-memory broadcast of x) and keeps them in registers for the rank-1 update;
+//   * the partial inner products x^T P_k are lane-local FMA chains; 3 shuffles fold the 4 row groups
+//     so that lane k ends up with column k (norm for lane j, trailing products for lanes > j,
+//     compact-WY T-factor products for lanes < j);
 //   * the column loop is a RUNTIME loop (no register array is indexed by j), so the kernel is a few
 //     KB of code instead of 250 KB -- the fully unrolled first version was instruction-fetch bound.
 // Reflector columns are kept UNSCALED (u = x, pivot entry implied) during the 32 steps and scaled by
@@ -98,6 +99,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return y;
 }
 
+// One Householder column step for the body warps, slot JI (= j >> 3) static so that the register array
+// is never indexed dynamically.  Lane (cg, rg) holds rows 8rg..8rg+7 of columns cg, cg+8, cg+16, cg+24.
+#define PL_SLOT_SWITCH(ji, STMT)                                                              \
+  switch (ji) { case 0: { constexpr int JI = 0; STMT } break; case 1: { constexpr int JI = 1; STMT } break; \
+                case 2: { constexpr int JI = 2; STMT } break; default: { constexpr int JI = 3; STMT } break; }
+
 #ifdef PL_PANEL_TIMING
 __device__ unsigned long long g_panel_dbg[8];
 extern "C" int pl_debug_panel_read(unsigned long long* out) {
@@ -107,9 +114,15 @@ extern "C" int pl_debug_panel_read(unsigned long long* out) {
   cudaMemcpyToSymbol(g_panel_dbg, z, sizeof(z));
   return 0;
 }
-#define PT_MARK(k) do { long long _t = clock64(); if (lane == 0 && warp == PT_WARP) atomicAdd(&g_panel_dbg[k], (unsigned long long)(_t - tprev)); tprev = _t; } while (0)
+#define PT_DECL long long tacc0 = 0, tacc1 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tprev = clock64();
+#define PT_MARK(k) do { long long _t = clock64(); tacc##k += _t - tprev; tprev = _t; } while (0)
+#define PT_FLUSH do { if (lane == 0 && warp == PT_WARP) { atomicAdd(&g_panel_dbg[0], (unsigned long long)tacc0); atomicAdd(&g_panel_dbg[1], (unsigned long long)tacc1); \
+  atomicAdd(&g_panel_dbg[2], (unsigned long long)tacc2); atomicAdd(&g_panel_dbg[3], (unsigned long long)tacc3); atomicAdd(&g_panel_dbg[4], (unsigned long long)tacc4); \
+  atomicAdd(&g_panel_dbg[5], (unsigned long long)tacc5); } } while (0)
 #else
+#define PT_DECL
 #define PT_MARK(k)
+#define PT_FLUSH
 #endif
 template <int MINB>
 __global__ void __launch_bounds__(160, MINB)
@@ -124,10 +137,12 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
   __shared__ __align__(16) double zsm[32];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = lane & 7, rg = lane >> 3;     // body warps: column group / row group of this lane
   const int64_t t0 = (int64_t)blockIdx.x * s;
   const int64_t pivblk = t0 * G;
-  double a[32];          // body warps: column `lane` of this warp's NB x NB block
-  double mysc = 0.0;
+  double a[4][8];        // body warps: a[i][r] = P[8*rg + r][cg + 8*i] of this warp's NB x NB block
+  double mysc = 0.0;     // 1/(alpha-beta) of column `lane` (every lane owns the bookkeeping of one column)
+  PT_DECL
 
   if (warp == 0) {   // pivot block -> shared memory (row-wise, coalesced)
     const double* src = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
@@ -147,37 +162,41 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
     if (warp >= 1) q = (i == 0) ? (warp <= 3 ? warp : -1) : (warp - 1);
     const int64_t kblk = t * G + q;
     const bool valid = (q >= 0) && (kblk < nblk);
-    double* blkp = Vb + (row0 + (valid ? kblk : 0) * bs) * ld + col0 + lane;
+    double* blkp = Vb + (row0 + (valid ? kblk : 0) * bs + 8 * rg) * ld + col0 + cg;
     if (warp >= 1) {
       if (valid) {
 #pragma unroll
-        for (int r = 0; r < 32; r++) a[r] = blkp[(int64_t)r * ld];
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) a[ii][r] = blkp[(int64_t)r * ld + 8 * ii];
         if (upper) {
 #pragma unroll
-          for (int r = 0; r < 32; r++) if (r > lane) a[r] = 0.0;
+          for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) if (8 * rg + r > cg + 8 * ii) a[ii][r] = 0.0;
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 32; r++) a[r] = 0.0;
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) a[ii][r] = 0.0;
       }
     }
     for (int e = threadIdx.x; e < 32 * 33; e += 160) (&Ts[0][0])[e] = 0.0;
     mysc = 0.0;
-    if (warp >= 1 && lane == 0) {   // column 0 of the body blocks for step 0 (later columns are pre-published)
+    if (warp >= 1 && cg == 0) {   // column 0 of the body blocks for step 0 (later columns are pre-published)
 #pragma unroll
-      for (int r = 0; r < 32; r += 2) *reinterpret_cast<double2*>(&xs[0][warp][r]) = make_double2(a[r], a[r + 1]);
+      for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(&xs[0][warp][8 * rg + r]) = make_double2(a[0][r], a[0][r + 1]);
     }
     __syncthreads();
 
-#ifdef PL_PANEL_TIMING
-    long long tprev = clock64();
-#endif
+    PT_MARK(0);
 #pragma unroll 1
     for (int j = 0; j < 32; j++) {
       const int buf = j & 1;
-      PT_MARK(0);
-      // 1. publish column j of this warp's block and form the lane-local inner products x^T P_lane
+      double x[8];       // body warps: the pivot column restricted to this lane's 8 rows
       double dsum = 0.0;
+      // 1. lane-local partial inner products x^T P_k and their reduction over the 4 row groups
       if (warp == 0) {
         prow[buf][lane] = Rs[j][lane];
         if (dense_piv) {
@@ -194,29 +213,45 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
           dsum = (d0 + d1) + (d2 + d3);
         }
       } else {
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, d5 = 0.0, d6 = 0.0, d7 = 0.0;
 #pragma unroll
-        for (int r = 0; r < 32; r += 8) {
-          const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][warp][r]);
-          const double2 xb = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 2]);
-          const double2 xc = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 4]);
-          const double2 xd = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 6]);
-          d0 = fma(xa.x, a[r], d0); d1 = fma(xa.y, a[r + 1], d1);
-          d2 = fma(xb.x, a[r + 2], d2); d3 = fma(xb.y, a[r + 3], d3);
-          d4 = fma(xc.x, a[r + 4], d4); d5 = fma(xc.y, a[r + 5], d5);
-          d6 = fma(xd.x, a[r + 6], d6); d7 = fma(xd.y, a[r + 7], d7);
+        for (int r = 0; r < 8; r += 2) {
+          const double2 xv = *reinterpret_cast<const double2*>(&xs[buf][warp][8 * rg + r]);
+          x[r] = xv.x; x[r + 1] = xv.y;
         }
-        dsum = ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+        double p[4], pb[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) { p[ii] = 0.0; pb[ii] = 0.0; }
+#pragma unroll
+        for (int r = 0; r < 8; r += 2)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) { p[ii] = fma(x[r], a[ii][r], p[ii]); pb[ii] = fma(x[r + 1], a[ii][r + 1], pb[ii]); }
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) p[ii] += pb[ii];
+        // transposed reduction over the row groups: lane (cg, rg) ends with the total of column cg + 8*rg = lane
+        const bool hi2 = (rg & 2) != 0, hi1 = (rg & 1) != 0;
+        const double s0 = hi2 ? p[0] : p[2], s1 = hi2 ? p[1] : p[3];
+        const double k0 = hi2 ? p[2] : p[0], k1 = hi2 ? p[3] : p[1];
+        const double q0 = k0 + __shfl_xor_sync(FULL, s0, 16), q1 = k1 + __shfl_xor_sync(FULL, s1, 16);
+        const double s2 = hi1 ? q0 : q1, k2 = hi1 ? q1 : q0;
+        dsum = k2 + __shfl_xor_sync(FULL, s2, 8);
       }
       PT_MARK(1);
       red[buf][warp][lane] = dsum;
+#ifdef PL_SKIP_BAR
+      __syncwarp();
+#else
       __syncthreads();
+#endif
       PT_MARK(2);
       const double tot = (red[buf][0][lane] + red[buf][1][lane]) + (red[buf][2][lane] + red[buf][3][lane]) + red[buf][4][lane];
       const double alpha = prow[buf][j];
       const double sigma2 = __shfl_sync(FULL, tot, j);
       double beta = alpha, tau = 0.0, scale = 0.0;
+#ifdef PL_SKIP_SCALARS
+      if (false) {
+#else
       if (sigma2 != 0.0) {
+#endif
         const double s2 = fma(alpha, alpha, sigma2);
         if (s2 > 1e-280 && s2 < 1e280) {
           // |beta| = sqrt(s2), scale = 1/(alpha - beta) = sgn/(|alpha| + |beta|), tau = (|alpha| + |beta|)/|beta|.
@@ -243,11 +278,11 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
         }
       }
       if (lane == j) mysc = scale;
-      PT_MARK(3);
       const double zz = fma(scale, tot, prow[buf][lane]);
       const double w = (lane > j) ? tau * zz : 0.0;
-      // 2. trailing update of this lane's column: P[r][lane] -= (x_r * scale) * w
+      // 2. trailing update P[r][k] -= (x_r * scale) * w_k, and pre-publication of the next pivot column
       const double sw = scale * w;
+      PT_MARK(3);
       if (warp == 0) {
         if (dense_piv) {
 #pragma unroll
@@ -259,22 +294,27 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
         }
         Rs[j][lane] = (lane == j) ? beta : (Rs[j][lane] - w);    // pivot row (v = 1), new diagonal
       } else {
-        const bool next = (lane == j + 1);      // this lane owns the next pivot column: pre-publish it
+        double swi[4];
 #pragma unroll
-        for (int r = 0; r < 32; r += 4) {
-          const double2 xa = *reinterpret_cast<const double2*>(&xs[buf][warp][r]);
-          const double2 xb = *reinterpret_cast<const double2*>(&xs[buf][warp][r + 2]);
-          a[r] = fma(-xa.x, sw, a[r]); a[r + 1] = fma(-xa.y, sw, a[r + 1]);
-          a[r + 2] = fma(-xb.x, sw, a[r + 2]); a[r + 3] = fma(-xb.y, sw, a[r + 3]);
-          if (next) {
-            *reinterpret_cast<double2*>(&xs[buf ^ 1][warp][r]) = make_double2(a[r], a[r + 1]);
-            *reinterpret_cast<double2*>(&xs[buf ^ 1][warp][r + 2]) = make_double2(a[r + 2], a[r + 3]);
-          }
+        for (int ii = 0; ii < 4; ii++) swi[ii] = __shfl_sync(FULL, sw, cg + 8 * ii);
+#ifndef PL_SKIP_UPDATE
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) a[ii][r] = fma(-x[r], swi[ii], a[ii][r]);
+#endif
+        const int jn = j + 1;
+        if (jn < 32 && cg == (jn & 7)) {   // the 4 lanes (one per row group) that hold the next pivot column
+          PL_SLOT_SWITCH(jn >> 3,
+            _Pragma("unroll") for (int r = 0; r < 8; r += 2)
+              *reinterpret_cast<double2*>(&xs[buf ^ 1][warp][8 * rg + r]) = make_double2(a[JI][r], a[JI][r + 1]);
+          )
         }
       }
       PT_MARK(4);
       // 3. compact-WY T, column j:  T[0:j,j] = -tau * T[0:j,0:j] * z ,  T[j][j] = tau.
       //    Columns >= j of Ts are still zero, so the sum runs over all 32 entries (static unroll).
+#ifndef PL_SKIP_T
       if (warp == twarp) {
         zsm[lane] = (lane < j) ? mysc * zz : 0.0;
         __syncwarp();
@@ -290,11 +330,11 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
         if (lane < j) Ts[lane][j] = -tau * acc;
         if (lane == j) Ts[lane][j] = tau;
       }
+#endif
       __syncwarp();
       PT_MARK(5);
     }
     __syncthreads();
-    PT_MARK(6);
 
     // ---- scale the reflector columns, write reflectors and T
     if (warp == 0) {
@@ -305,14 +345,20 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
       __syncwarp();
     } else {
 #pragma unroll
-      for (int r = 0; r < 32; r++) a[r] *= mysc;
+      for (int ii = 0; ii < 4; ii++) {
+        const double sc = __shfl_sync(FULL, mysc, cg + 8 * ii);
+#pragma unroll
+        for (int r = 0; r < 8; r++) a[ii][r] *= sc;
+      }
     }
     double* Tt = Tl + t * (NB * NB);
     for (int e = threadIdx.x; e < NB * NB; e += 160) Tt[e] = Ts[e >> 5][e & 31];
     if (!upper) {
       if (warp >= 1 && valid) {
 #pragma unroll
-        for (int r = 0; r < 32; r++) blkp[(int64_t)r * ld] = a[r];
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) blkp[(int64_t)r * ld + 8 * ii] = a[ii][r];
       }
       if (warp == 0 && i == 0) {   // explicit unit-lower pivot-block reflectors -> side store (the in-place
         double* dst = Vpivl + (int64_t)blockIdx.x * (NB * NB) + lane;   // rows are reused when Q is formed)
@@ -322,9 +368,11 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
     } else {
       double* Vt = Vupl + t * (TB * NB);
       if (warp >= 1 && q >= 0) {   // body block q of the tile (zeros when the block is missing)
-        double* dst = Vt + (q * NB) * NB + lane;
+        double* dst = Vt + (q * NB + 8 * rg) * NB + cg;
 #pragma unroll
-        for (int r = 0; r < 32; r++) dst[r * NB] = a[r];
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++) dst[r * NB + 8 * ii] = a[ii][r];
       }
       if (i == 0 && warp == 0) {   // explicit unit-lower pivot block
         double* dst = Vt + lane;
@@ -344,6 +392,7 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
 #pragma unroll 8
     for (int r = 0; r < 32; r++) if (r <= lane) dst[(int64_t)r * ld] = Rs[r][lane];
   }
+  PT_FLUSH;
 }
 
 // =============================================================================================
@@ -436,38 +485,52 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       cp_async16(&S.Ts[r_lo + 16][c2], tp + 16 * NB, true);
     }
     cp_async_commit();
+    if (it + 1 < cnt) {   // pull the next tile's rows into L2 while this tile computes (128 rows x 256 B each)
+      const int64_t tn = A.forward ? t + 1 : t - 1;
+      const int pr = tid >> 1, ph = (tid & 1) * 16;   // row of the tile, 128-byte half of the 256-byte row
+      const int pq = pr >> 5, prr = pr & 31;
+      if ((tn * G + pq) < A.nblk) {
+        const double* cpf = Cb + (A.row0 + (tn * G + pq) * A.bs + prr) * ldc + coff + ph;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cpf));
+        const double* vpf = upper ? (A.Vupl + (tn * TB + pr) * NB + ph)
+                                  : (A.Vb + (A.row0 + (tn * G + pq) * A.bs + prr) * A.ld + A.col0 + ph);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vpf));
+      }
+    }
     cp_async_wait<0>();
     __syncthreads();
     const double (*C0)[SP] = first ? S.Zs : S.Cs[0];   // slab 0 of the first tile is the carried block
 
-    // ---- GEMM1: W = V^T C (+ Z)      two independent accumulator chains (even / odd k16 steps)
+    // ---- GEMM1: W = V^T C (+ Z)      four independent accumulator chains (one per slab)
     {
-      double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+      double acc[G][4];
 #pragma unroll
-      for (int q = 0; q < G; q++) {
-        const double (*Cq)[SP] = (q == 0) ? C0 : S.Cs[q];
-        double fa[8], fb[4];
+      for (int q = 0; q < G; q++) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
 #pragma unroll
-        for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1)][16 * mb + g + 8 * (x & 1)];
+      for (int kk = 0; kk < 2; kk++) {
 #pragma unroll
-        for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x][8 * ng + g];
-        mma16816(acc0, fa, fb);
+        for (int q = 0; q < G; q++) {
+          const double (*Cq)[SP] = (q == 0) ? C0 : S.Cs[q];
+          double fa[8], fb[4];
 #pragma unroll
-        for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16][16 * mb + g + 8 * (x & 1)];
+          for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16 * kk][16 * mb + g + 8 * (x & 1)];
 #pragma unroll
-        for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16][8 * ng + g];
-        mma16816(acc1, fa, fb);
+          for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16 * kk][8 * ng + g];
+          mma16816(acc[q], fa, fb);
+        }
       }
       const int r = 16 * mb + g, c = 8 * ng + 2 * t4;
       double2 z01 = make_double2(0.0, 0.0), z23 = make_double2(0.0, 0.0);
       if (!first) { z01 = *reinterpret_cast<const double2*>(&S.Zs[r][c]); z23 = *reinterpret_cast<const double2*>(&S.Zs[r + 8][c]); }
-      *reinterpret_cast<double2*>(&S.Ws[r][c]) = make_double2((acc0[0] + acc1[0]) + z01.x, (acc0[1] + acc1[1]) + z01.y);
-      *reinterpret_cast<double2*>(&S.Ws[r + 8][c]) = make_double2((acc0[2] + acc1[2]) + z23.x, (acc0[3] + acc1[3]) + z23.y);
+      *reinterpret_cast<double2*>(&S.Ws[r][c]) = make_double2(((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0])) + z01.x,
+                                                               ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1])) + z01.y);
+      *reinterpret_cast<double2*>(&S.Ws[r + 8][c]) = make_double2(((acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2])) + z23.x,
+                                                                   ((acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3])) + z23.y);
     }
     __syncthreads();
     // ---- W' = op(T) W     forward: T^T, backward: T
     {
-      double acc[4] = {0, 0, 0, 0};
+      double acc[4] = {0, 0, 0, 0}, accb[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int kk = 0; kk < 2; kk++) {
         double fa[8], fb[4];
@@ -480,8 +543,10 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
         }
 #pragma unroll
         for (int x = 0; x < 4; x++) fb[x] = S.Ws[t4 + 4 * x + 16 * kk][8 * ng + g];
-        mma16816(acc, fa, fb);
+        if (kk == 0) mma16816(acc, fa, fb); else mma16816(accb, fa, fb);
       }
+#pragma unroll
+      for (int x = 0; x < 4; x++) acc[x] += accb[x];
       const int r = 16 * mb + g, c = 8 * ng + 2 * t4;
       *reinterpret_cast<double2*>(&S.Wp[r][c]) = make_double2(acc[0], acc[1]);
       *reinterpret_cast<double2*>(&S.Wp[r + 8][c]) = make_double2(acc[2], acc[3]);

@@ -114,7 +114,7 @@ GLOO_SCRIPT = textwrap.dedent("""
     assert torch.equal(Sg[0], Sg[1])            # identical on all ranks
     assert abs(float(parall.mpi_reduce(1.0)) - 2.0) < 1e-15
     dist.barrier(); dist.destroy_process_group()
-    sys.stdout.write('RANK_OK_%d\n' % rank); sys.stdout.flush()
+    print('RANK_OK_%d' % rank, flush=True)
 """)
 
 

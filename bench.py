@@ -11,7 +11,8 @@ with `worksplit`) and the step contains the single NCCL all-gather of the R fact
 value          = algorithmic GFLOP/s of the whole job, F_alg = 4 m n^2, inputs
                  resident in HBM, CUDA-event timed, max over ranks.
 e2e            = same metric through the host-pointer C ABI call (pl_tsqr_svd_host_f64: the
-                 drop-in for the reference's dtsqr_svd), host<->device copies inside the timed region.
+                 drop-in for the reference's dtsqr_svd), host<->device copies inside the timed region
+                 (pinned host buffers; the library caches its device buffers after the first call).
 roofline       = dominant kernel (caqr_update_kernel, FP64 DMMA block-reflector application),
                  per-launch CUDA-event timing from the library's profiling hooks.
 cpu_baseline   = the reference's own C sources (oracle/_ref, LAPACKE+CBLAS on scipy-openblas) on the
@@ -296,7 +297,7 @@ def run_ours(args):
         e2e = {"value": f_alg(m_e2e * size, n) / dt * 1e-9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": m_e2e * n * 8, "d2h_bytes_per_step": m_e2e * n * 8 + n * 8 + n * n * 8,
                "rows_per_gpu": m_e2e, "ms_per_step": dt * 1e3,
-               "path": "pl_tsqr_svd_host_f64 (host pointers, cudaMalloc + H2D + compute + D2H inside the timed region)" if size == 1
+               "path": "pl_tsqr_svd_host_f64 (host pointers; chunked H2D + compute + chunked D2H inside the timed region, device buffers cached by the library after the warm-up call)" if size == 1
                        else "pyloworder_b200.math.tsqr_svd on pinned host tensors (H2D + compute + D2H inside the timed region)"}
     except Exception as ex:  # host memory too small etc.
         e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}

@@ -270,17 +270,54 @@ int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, in
   PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
   const size_t ab = (size_t)m * n * 8, wsb = pl_qr_workspace_bytes(m, n);
   void *dA = nullptr, *dU = nullptr, *dS = nullptr, *dV = nullptr, *ws = nullptr;
-  cudaStream_t st = nullptr;
   int rc;
   if ((rc = hc_get(0, ab, &dA)) || (rc = hc_get(1, ab, &dU)) || (rc = hc_get(2, (size_t)n * 8, &dS)) ||
       (rc = hc_get(3, (size_t)n * n * 8, &dV)) || (rc = hc_get(4, wsb, &ws))) { pl_host_cache_free(); return rc; }
-  PL_CUDA(cudaMemcpyAsync(dA, Ai, ab, cudaMemcpyHostToDevice, st));
-  rc = pl_tsqr_svd_f64((double*)dU, (double*)dS, (double*)dV, (const double*)dA, m, n, ws, wsb, st);
+  static cudaStream_t st = nullptr, cs = nullptr;          // compute / copy streams of the host entry point
+  if (!st) { PL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); PL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)); }
+  WsLayout L = make_layout(m, n);
+  const Plan& P = L.plan;
+  // ---- H2D in row chunks on the copy stream; the padding copy of a chunk starts as soon as it has landed
+  const int NCH = 8;
+  cudaEvent_t ev[NCH];
+  for (int c = 0; c < NCH; c++) PL_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+  double* Vb = at(ws, L.vb);
+  for (int c = 0; c < NCH; c++) {
+    const int64_t r0 = m * c / NCH, r1 = m * (c + 1) / NCH;
+    if (r1 <= r0) continue;
+    PL_CUDA(cudaMemcpyAsync((double*)dA + r0 * n, Ai + r0 * n, (size_t)(r1 - r0) * n * 8, cudaMemcpyHostToDevice, cs));
+    PL_CUDA(cudaEventRecord(ev[c], cs));
+    PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+    rc = copy_pad(Vb + r0 * P.npad, P.npad, (const double*)dA + r0 * n, n, r1 - r0, n, P.npad, st);
+    if (rc) return rc;
+  }
+  PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
+  // ---- factor, small SVD, explicit Q (all on the compute stream)
+  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
   if (rc) return rc;
-  PL_CUDA(cudaMemcpyAsync(Ui, dU, ab, cudaMemcpyDeviceToHost, st));
+  double* R = at(ws, L.r);
+  double* Ur = at(ws, L.ur);
+  if ((rc = caqr_extract_r(P, Vb, R, n, st))) return rc;
+  if ((rc = svd_small(Ur, n, (double*)dS, (double*)dV, n, R, n, n, at(ws, L.svd), nullptr, st))) return rc;
+  if ((rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st))) return rc;
+  const int64_t kp = round_up(n, 16), np = round_up(n, 64);
+  double* Bp = at(ws, L.bp);
+  if ((rc = pad_small(Bp, kp, np, Ur, n, n, n, nullptr, st))) return rc;
+  // ---- back-multiply in row chunks; the D2H of a chunk overlaps the GEMM of the next one
+  for (int c = 0; c < NCH; c++) {
+    const int64_t r0 = m * c / NCH, r1 = m * (c + 1) / NCH;
+    if (r1 <= r0) continue;
+    rc = gemm_tall((double*)dU + r0 * n, n, Vb + r0 * P.npad, P.npad, Bp, np, r1 - r0, n, kp, st);
+    if (rc) return rc;
+    PL_CUDA(cudaEventRecord(ev[c], st));
+    PL_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
+    PL_CUDA(cudaMemcpyAsync(Ui + r0 * n, (double*)dU + r0 * n, (size_t)(r1 - r0) * n * 8, cudaMemcpyDeviceToHost, cs));
+  }
   PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
   PL_CUDA(cudaStreamSynchronize(st));
+  PL_CUDA(cudaStreamSynchronize(cs));
+  for (int c = 0; c < NCH; c++) cudaEventDestroy(ev[c]);
   return 0;
 }
 

@@ -92,6 +92,19 @@ int pl_pod_run_f64(double* U, double* S, double* VT, double* X_mean, const doubl
 int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S, const double* VT, int64_t ldvt,
                        int64_t m, int64_t N, int64_t n, void* ws, size_t ws_bytes, void* stream);
 
+/* In-place variants (n % 32 == 0): the output buffer doubles as the factorisation buffer, so the footprint is
+ * A + U + T-factors (~2.3 x A instead of ~3.4 x A; what lets a 1.25e8 x 64 shard of BASELINE config 5 fit in 180 GB).
+ * Ubuf must hold pl_qr_inplace_rows(m, n) x n doubles; rows [0, m) are the result U (or Q), the tail is scratch.
+ * Same semantics as pl_qr_factor_f64 / pl_qr_apply_q_f64 / pl_pod_run_f64 otherwise. */
+int64_t pl_qr_inplace_rows(int64_t m, int64_t n);
+size_t pl_qr_workspace_bytes_inplace(int64_t m, int64_t n);
+int pl_qr_factor_inplace_f64(double* R, double* X_mean, double* Ubuf, const double* A, int64_t m, int64_t n, int center,
+                             void* ws, size_t ws_bytes, void* stream);
+int pl_qr_apply_q_inplace_f64(double* Ubuf, const double* W, int64_t ldw, int64_t m, int64_t n, int flags,
+                              void* ws, size_t ws_bytes, void* stream);
+int pl_pod_run_inplace_f64(double* Ubuf, double* S, double* VT, double* X_mean, const double* X, int64_t m, int64_t n,
+                           int remove_mean, void* ws, size_t ws_bytes, void* stream);
+
 /* Same signature and meaning as the reference's dtsqr_svd but HOST pointers (what a ctypes / Cython
  * binding of the reference would pass): allocates device memory, copies in, computes, copies back. */
 int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n);

@@ -9,7 +9,7 @@ L = _lib.lib()
 cases = [("cfg1 POD(remove_mean) 89,351 x 151 (full config)", 89351, 151, True, 2021),
          ("cfg3 shard POD(remove_mean) 24,000,000 x 256 (1/8 of 192M rows)", 24_000_000, 256, True, 2023),
          ("cfg4 shard tsqr_svd 2,000,000 x 999 (1/8 of 16M rows)", 2_000_000, 999, False, 2024),
-         ("cfg5 half shard tsqr_svd 62,500,000 x 64 (1/16 of 1e9 rows; a full 1.25e8-row shard needs the in-place variant)", 62_500_000, 64, False, 2025)]
+         ("cfg5 shard tsqr_svd 125,000,000 x 64 (1/8 of 1e9 rows, in-place variant: A 64 GB + U 64 GB + 20 GB workspace)", 125_000_000, 64, False, 2025)]
 out = []
 for name, m, n, pod, seed in cases:
     try:
@@ -24,6 +24,7 @@ for name, m, n, pod, seed in cases:
             U, S, V = fn(); del U
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
+        del S, V
         U, S, V = fn()
         orth = float((U[:200000].T @ U[:200000]).diagonal().sub(0).abs().max())
         I = torch.eye(n, dtype=torch.float64, device="cuda")

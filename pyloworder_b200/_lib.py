@@ -29,6 +29,11 @@ _SIGS = {
     "pl_qr_workspace_bytes": (_sz, [_i64, _i64]),
     "pl_qr_factor_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
     "pl_qr_apply_q_f64": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
+    "pl_qr_inplace_rows": (_i64, [_i64, _i64]),
+    "pl_qr_workspace_bytes_inplace": (_sz, [_i64, _i64]),
+    "pl_qr_factor_inplace_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
+    "pl_qr_apply_q_inplace_f64": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
+    "pl_pod_run_inplace_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
     "pl_svd_workspace_bytes": (_sz, [_i64]),
     "pl_svd_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "pl_tsqr_svd_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),

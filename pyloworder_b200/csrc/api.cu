@@ -29,15 +29,17 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 // ---- workspace layout for one tall matrix ---------------------------------------------------
 struct WsLayout {
   Plan plan;
-  size_t vb, tws, vup, vpiv, r, bp, ur, svd, vt, s, total;
+  size_t vb, tws, vup, vpiv, r, bp, ur, svd, vt, s, tmp, total;
+  bool ext_vb; int64_t tmp_rows;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-static WsLayout make_layout(int64_t m, int64_t n) {
+static WsLayout make_layout(int64_t m, int64_t n, bool ext_vb = false) {
   WsLayout L;
   L.plan = make_plan(m, n);
   const Plan& P = L.plan;
   size_t off = 0;
-  L.vb = off;   off += al((size_t)P.mrows * P.npad * 8);
+  L.ext_vb = ext_vb; L.tmp = 0; L.tmp_rows = 0;
+  L.vb = off;   if (!ext_vb) off += al((size_t)P.mrows * P.npad * 8);
   L.tws = off;  off += al((size_t)P.t_tiles * NB * NB * 8);
   L.vup = off;  off += al((size_t)(P.vup_tiles > 0 ? P.vup_tiles : 1) * TB * NB * 8);
   L.vpiv = off; off += al((size_t)P.vpiv_strips * NB * NB * 8);
@@ -48,6 +50,11 @@ static WsLayout make_layout(int64_t m, int64_t n) {
   L.vt = off;   off += al((size_t)n * n * 8);
   L.s = off;    off += al((size_t)n * 8);
   L.svd = off;  off += al((size_t)svd_small_scratch_doubles(n) * 8);
+  if (ext_vb) {   // row-chunk buffer of the in-place back-multiply (<= 2 GiB)
+    int64_t rows = (int64_t)(2147483648LL / 8) / P.npad;
+    rows = rows < 4096 ? 4096 : rows; if (rows > m) rows = m;
+    L.tmp_rows = rows; L.tmp = off; off += al((size_t)rows * P.npad * 8);
+  }
   L.total = off;
   return L;
 }
@@ -60,9 +67,9 @@ static int check_ws(const WsLayout& L, void* ws, size_t ws_bytes, int argpos) {
 }
 
 static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int64_t n, int center, void* ws,
-                     const WsLayout& L, cudaStream_t st, double* X_var = nullptr) {
+                     const WsLayout& L, cudaStream_t st, double* X_var = nullptr, double* Vb_ext = nullptr) {
   const Plan& P = L.plan;
-  double* Vb = at(ws, L.vb);
+  double* Vb = Vb_ext ? Vb_ext : at(ws, L.vb);
   int rc;
   {
     ProfScope ps(PROF_COPY, st);
@@ -79,9 +86,9 @@ static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int6
 }
 
 static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n, int flags,
-                      void* ws, const WsLayout& L, cudaStream_t st) {
+                      void* ws, const WsLayout& L, cudaStream_t st, double* Vb_ext = nullptr) {
   const Plan& P = L.plan;
-  double* Vb = at(ws, L.vb);
+  double* Vb = Vb_ext ? Vb_ext : at(ws, L.vb);
   int rc;
   if (!(flags & 1)) {
     rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
@@ -89,6 +96,7 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   }
   if (!W) {
     if (nw != n) { set_error("apply_q: W == NULL needs nw == n"); return -5; }
+    if (U == Vb) return 0;   // explicit Q already in place
     return copy_pad(U, ldu, Vb, P.npad, m, n, n, st);
   }
   if (nw > n) { set_error("apply_q: nw > n"); return -5; }
@@ -99,7 +107,17 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   ProfScope ps(PROF_GEMM, st);
   // k is rounded up to the packed height: the extra columns of Q1 (finite padding) meet zero rows of Bp,
   // and an even k keeps the 16-byte cp.async path for odd n
-  return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, kp, st);
+  if (U != Vb) return gemm_tall(U, ldu, Vb, P.npad, Bp, np, m, nw, kp, st);
+  // in place (U aliases the factorisation buffer): row chunks through a bounded temporary
+  if (!L.ext_vb || ldu != P.npad || nw != n) { set_error("apply_q: in-place product needs an external Vb with ld == n_pad == n"); return -1; }
+  double* tmp = at(ws, L.tmp);
+  for (int64_t r0 = 0; r0 < m; r0 += L.tmp_rows) {
+    const int64_t rows = (m - r0 < L.tmp_rows) ? (m - r0) : L.tmp_rows;
+    rc = gemm_tall(tmp, P.npad, Vb + r0 * P.npad, P.npad, Bp, np, rows, nw, kp, st);
+    if (rc) return rc;
+    PL_CUDA(cudaMemcpyAsync(Vb + r0 * P.npad, tmp, (size_t)rows * P.npad * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
 }
 }  // namespace pl
 
@@ -198,6 +216,49 @@ int pl_qr_apply_q_f64(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   int rc = check_ws(L, ws, ws_bytes, 9);
   if (rc) return rc;
   return qr_apply_q(U, ldu, W, ldw, nw, m, n, flags, ws, L, (cudaStream_t)stream);
+}
+
+/* ---- in-place variants: the caller's U buffer ((m + n + 32) x n doubles, n % 32 == 0) is the factorisation buffer */
+int64_t pl_qr_inplace_rows(int64_t m, int64_t n) { return (n > 0 && n % NB == 0) ? m + n + NB : 0; }
+size_t pl_qr_workspace_bytes_inplace(int64_t m, int64_t n) {
+  if (m <= 0 || n <= 0 || n % NB) return 0;
+  return make_layout(m, n, true).total;
+}
+int pl_qr_factor_inplace_f64(double* R, double* X_mean, double* Ubuf, const double* A, int64_t m, int64_t n, int center,
+                             void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n && n % NB == 0, 5, "need m >= n > 0 and n % 32 == 0");
+  PL_ARG(!center || X_mean, 2, "X_mean required when center != 0");
+  WsLayout L = make_layout(m, n, true);
+  int rc = check_ws(L, ws, ws_bytes, 8);
+  if (rc) return rc;
+  return qr_factor(R, X_mean, A, m, n, center, ws, L, (cudaStream_t)stream, nullptr, Ubuf);
+}
+int pl_qr_apply_q_inplace_f64(double* Ubuf, const double* W, int64_t ldw, int64_t m, int64_t n, int flags, void* ws,
+                              size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n && n % NB == 0, 5, "need m >= n > 0 and n % 32 == 0");
+  WsLayout L = make_layout(m, n, true);
+  int rc = check_ws(L, ws, ws_bytes, 7);
+  if (rc) return rc;
+  return qr_apply_q(Ubuf, n, W, ldw, n, m, n, flags, ws, L, (cudaStream_t)stream, Ubuf);
+}
+int pl_pod_run_inplace_f64(double* Ubuf, double* S, double* VT, double* X_mean, const double* X, int64_t m, int64_t n,
+                           int remove_mean, void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(n > 0 && m >= n && n % NB == 0, 7, "need m >= n > 0 and n % 32 == 0");
+  PL_ARG(!remove_mean || X_mean, 4, "X_mean required when remove_mean != 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  WsLayout L = make_layout(m, n, true);
+  int rc = check_ws(L, ws, ws_bytes, 9);
+  if (rc) return rc;
+  double* R = at(ws, L.r);
+  rc = qr_factor(R, X_mean, X, m, n, remove_mean ? 1 : 0, ws, L, st, nullptr, Ubuf);
+  if (rc) return rc;
+  double* Ur = at(ws, L.ur);
+  {
+    ProfScope ps(PROF_SVD, st);
+    rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
+  }
+  if (rc) return rc;
+  return qr_apply_q(Ubuf, n, Ur, n, n, m, n, 0, ws, L, st, Ubuf);
 }
 
 size_t pl_svd_workspace_bytes(int64_t n) { return (size_t)svd_small_scratch_doubles(n) * 8 + 256; }

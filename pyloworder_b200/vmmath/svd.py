@@ -11,6 +11,8 @@ Single rank: one C call (`pl_tsqr_svd_f64`).  P ranks (one process per GPU, torc
 TSQR is valid for any reduction tree (Demmel et al. 2012, the paper svd.py:58 cites), so the flat
 all-gather tree gives the same R up to row signs.  S and VT are identical on all ranks.
 """
+import os
+
 import torch
 
 from .. import _lib, _dev
@@ -28,23 +30,56 @@ def next_power_of_2(n):
     return p
 
 
+def _inplace_ok(m, n, device):
+    """Use the in-place variant (output buffer = factorisation buffer, ~2.3 x A instead of ~3.4 x A, one extra
+    device-to-device pass over U)?  Needs n % 32 == 0; chosen when the out-of-place buffers would not fit in
+    the free device memory (PL_INPLACE=1 / PL_NO_INPLACE=1 force the choice)."""
+    if n % 32 != 0 or os.environ.get("PL_NO_INPLACE"):
+        return False
+    if os.environ.get("PL_INPLACE"):
+        return True
+    need = _lib.lib().pl_qr_workspace_bytes(m, n) + m * n * 8
+    free, _ = torch.cuda.mem_get_info(device)
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return need > 0.92 * free
+
+
 class CudaEngine:
     """The device operations the multi-rank composition needs; tests inject a CPU stand-in."""
+
+    def __init__(self):
+        self._ubuf = {}      # tag -> (m + n + 32) x n buffer that holds the reflectors / Q / U of the in-place path
 
     def factor(self, A, tag, center=False):
         m, n = A.shape
         L = _lib.lib()
-        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, A.device)
         R = torch.empty((n, n), dtype=torch.float64, device=A.device)
         mean = torch.empty(m, dtype=torch.float64, device=A.device) if center else None
-        _lib.check(L.pl_qr_factor_f64(R.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n, int(center), wp, wb, _dev.stream()),
-                   "qr_factor")
+        if _inplace_ok(m, n, A.device):
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes_inplace(m, n), tag, A.device)
+            ubuf = torch.empty((L.pl_qr_inplace_rows(m, n), n), dtype=torch.float64, device=A.device)
+            _lib.check(L.pl_qr_factor_inplace_f64(R.data_ptr(), _dev.ptr(mean), ubuf.data_ptr(), A.data_ptr(), m, n, int(center),
+                                                  wp, wb, _dev.stream()), "qr_factor")
+            self._ubuf[tag] = ubuf
+        else:
+            self._ubuf.pop(tag, None)
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, A.device)
+            _lib.check(L.pl_qr_factor_f64(R.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n, int(center), wp, wb, _dev.stream()),
+                       "qr_factor")
         return R, mean
 
     def apply_q(self, shape, W, tag, device):
         """U = Q1 W for the matrix last factored under `tag` (W None -> explicit Q1)."""
         m, n = shape
         L = _lib.lib()
+        ubuf = self._ubuf.pop(tag, None)
+        if ubuf is not None:
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes_inplace(m, n), tag, device)
+            if W is not None and (W.shape[0] != n or W.shape[1] != n):
+                raise ValueError("apply_q: W must be n x n")
+            ldw = 0 if W is None else W.stride(0)
+            _lib.check(L.pl_qr_apply_q_inplace_f64(ubuf.data_ptr(), _dev.ptr(W), ldw, m, n, 0, wp, wb, _dev.stream()), "qr_apply_q")
+            return ubuf[:m]
         _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, device)
         nw = n if W is None else W.shape[1]
         U = torch.empty((m, nw), dtype=torch.float64, device=device)
@@ -65,11 +100,17 @@ class CudaEngine:
     def tsqr_svd_single(self, A, center=False):
         m, n = A.shape
         L = _lib.lib()
-        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), "local", A.device)
-        U = torch.empty((m, n), dtype=torch.float64, device=A.device)
         S = torch.empty(n, dtype=torch.float64, device=A.device)
         VT = torch.empty((n, n), dtype=torch.float64, device=A.device)
         mean = torch.empty(m, dtype=torch.float64, device=A.device) if center else None
+        if _inplace_ok(m, n, A.device):
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes_inplace(m, n), "local", A.device)
+            ubuf = torch.empty((L.pl_qr_inplace_rows(m, n), n), dtype=torch.float64, device=A.device)
+            _lib.check(L.pl_pod_run_inplace_f64(ubuf.data_ptr(), S.data_ptr(), VT.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n,
+                                                int(center), wp, wb, _dev.stream()), "tsqr_svd")
+            return ubuf[:m], S, VT, mean
+        _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), "local", A.device)
+        U = torch.empty((m, n), dtype=torch.float64, device=A.device)
         _lib.check(L.pl_pod_run_f64(U.data_ptr(), S.data_ptr(), VT.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n,
                                     int(center), wp, wb, _dev.stream()), "tsqr_svd")
         return U, S, VT, mean

@@ -249,6 +249,19 @@ def test_large_properties(pl):
     assert float((X - A).abs().max()) <= 1e-11
 
 
+def test_inplace_variant_matches(pl, monkeypatch):
+    """The memory-saving in-place path (output buffer = factorisation buffer) gives the same answer."""
+    A = synth.snapshots(30000, 96, 4)
+    monkeypatch.setenv("PL_NO_INPLACE", "1")
+    U0, S0, V0 = [host(t) for t in pl.POD.run(dev(A), remove_mean=True)]
+    monkeypatch.delenv("PL_NO_INPLACE"); monkeypatch.setenv("PL_INPLACE", "1")
+    U1, S1, V1 = [host(t) for t in pl.POD.run(dev(A), remove_mean=True)]
+    Q1, R1 = [host(t) for t in pl.math.qr(dev(A))]
+    assert np.abs(S0 - S1).max() <= 1e-14 * S0[0]
+    assert np.abs(U0 - U1).max() <= 1e-13 and np.abs(V0 - V1).max() <= 1e-13
+    assert np.abs(Q1 @ R1 - A).max() <= 1e-12 * np.abs(A).max()
+
+
 def test_native_library_is_the_one_running(pl):
     from pyloworder_b200 import _lib
     before = _lib.lib().pl_launch_count()

@@ -313,11 +313,13 @@ def run_ours(args):
         if size == 1 and not args.no_cpu:
             cb = cpu_reference(args.cpu_rows, n, 1, 0)
         value = f_alg(m_global, n) / (ms * 1e-3) * 1e-9
+        cfg_name = "BASELINE configs[1]" if (args.rows == ROWS_PER_GPU and n == N_COLS) else \
+                   ("BASELINE configs[4] 'billionaire' when run on 8 GPUs" if (args.rows == 125_000_000 and n == 64) else "custom shape")
         line = {"metric": "tsqr_svd_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"tsqr_svd of synthetic {args.rows}x{n} fp64 per GPU (BASELINE configs[1]; global {m_global}x{n}, rows sharded)",
-                           "rows_per_gpu": args.rows, "cols": n, "seed": SEED, "l2": "inputs (32.8 GB/GPU) larger than L2",
+                "config": {"workload": f"tsqr_svd of synthetic {args.rows}x{n} fp64 per GPU ({cfg_name}; global {m_global}x{n}, rows sharded)",
+                           "rows_per_gpu": args.rows, "cols": n, "seed": SEED, "l2": f"inputs ({args.rows * n * 8 / 1e9:.1f} GB/GPU) larger than L2",
                            "f_alg": "4*m*n^2"},
                 "rows_snapshots_per_s": m_global * n / (ms * 1e-3),
                 "frac_of_fp64_roofline": value * 1e-3 / (PEAK_FP64_TFLOPS * size),

@@ -265,12 +265,16 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": ach / PEAK_FP64_TFLOPS,
                 "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/r01_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry",
                 "avg_launch_ms": upd_ms / max(upd_launch, 1), "launches_per_step": upd_launch,
-                "share_of_step": upd_ms / sum(msb), "traffic": None}
+                "share_of_step": upd_ms / sum(msb), "traffic": None,
+                "ncu_traffic": {"launch": "first factor-pass launch of the 1,000,000 x 512 probe (15 chunks x 977 strips), profiles/r01_ncu_update_v2.txt",
+                                "dram_bytes": 7.948e9, "algorithmic_bytes": 7.94e9}}
 
     # ---- e2e through the host-pointer C ABI (rank 0 of N; every rank does its own shard)
     e2e = None
     del S, V
-    m_e2e = min(m, args.e2e_rows)
+    # host memory: 2 pinned buffers of m_e2e x n per rank; with several ranks on one node the e2e sample is capped
+    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else 1_000_000)
+    m_e2e = min(m, e2e_rows)
     try:
         host_in = torch.empty((m_e2e, n), dtype=torch.float64, pin_memory=True)
         host_in.copy_(A[:m_e2e])
@@ -342,7 +346,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
-    ap.add_argument("--e2e-rows", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU of the e2e leg (0: full shard on 1 GPU, 1M per GPU otherwise)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -264,6 +264,55 @@ __global__ void __launch_bounds__(128) svd_scatter_kernel(double* Ur, int64_t ld
   }
 }
 
+// Exactly zero singular values (zero rows of G, e.g. an all-zero snapshot column): LAPACK returns an arbitrary
+// orthonormal completion of V^T; do the same.  One CTA; for every zero row try the unit vectors e_0, e_1, ...,
+// orthogonalise twice against all rows already in place and keep the first candidate that survives.
+__global__ void __launch_bounds__(256) svd_complete_kernel(double* VT, int64_t ldvt, const double* S, int n) {
+  __shared__ double sh[8];
+  __shared__ double s_dot;
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  auto bsum = [&](double v) {
+    v = warp_sum(v);
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int i = 0; i < 8; i++) t += sh[i]; s_dot = t; }
+    __syncthreads();
+    return s_dot;
+  };
+  int cand = 0;
+  for (int z = 0; z < n; z++) {
+    if (S[z] != 0.0) continue;           // rows are sorted: zeros are at the end, earlier rows are complete
+    double* vz = VT + (int64_t)z * ldvt;
+    for (; cand < n; cand++) {
+      for (int j = tid; j < n; j += 256) vz[j] = (j == cand) ? 1.0 : 0.0;
+      __syncthreads();
+      for (int pass = 0; pass < 2; pass++) {
+        for (int r = 0; r < z; r++) {
+          const double* vr = VT + (int64_t)r * ldvt;
+          double d = 0.0;
+          for (int j = tid; j < n; j += 256) d += vz[j] * vr[j];
+          d = bsum(d);
+          for (int j = tid; j < n; j += 256) vz[j] -= d * vr[j];
+          __syncthreads();
+        }
+      }
+      double nn = 0.0;
+      for (int j = tid; j < n; j += 256) nn += vz[j] * vz[j];
+      nn = bsum(nn);
+      if (tid == 0) s_ok = nn > 0.25;
+      __syncthreads();
+      if (s_ok) {
+        const double inv = 1.0 / sqrt(nn);
+        for (int j = tid; j < n; j += 256) vz[j] *= inv;
+        __syncthreads();
+        cand++;
+        break;
+      }
+    }
+  }
+}
+
 int64_t svd_small_scratch_doubles(int64_t n) { return 2 * n * n + 2 * n + 64; }
 
 int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, const double* R, int64_t ldr, int64_t n,
@@ -339,6 +388,10 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   svd_scatter_kernel<<<ni, 128, 0, st>>>(Ur, ldu, S, VT, ldvt, Gm, J, s, rank, ni);
   PL_LAUNCH_CHECK();
   count_launches(2);
+  if (ldvt == n || true) {   // fill the rows of V^T that belong to exactly zero singular values
+    svd_complete_kernel<<<1, 256, 0, st>>>(VT, ldvt, S, ni);
+    PL_LAUNCH_CHECK();
+  }
   if (sweeps_out) *sweeps_out = sweeps;
   if (getenv("PL_DEBUG")) fprintf(stderr, "[pl] svd_small n=%d sweeps=%d\n", ni, sweeps);
   return 0;

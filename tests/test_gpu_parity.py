@@ -196,6 +196,23 @@ def test_qr_and_svd_entry_points(pl):
     assert np.max(np.abs(S - So) / So) <= 1e-10
 
 
+def test_exactly_rank_deficient_input(pl):
+    """All-zero trailing snapshot columns give exactly zero singular values; U and V must stay orthonormal
+    (LAPACK returns an arbitrary orthonormal completion, so only the invariants are compared)."""
+    A = synth.random_matrix(4000, 40, 3)
+    A[:, 37:] = 0.0
+    A[:, 5] = A[:, 4]                      # and one exactly duplicated column
+    U, S, V = [host(t) for t in pl.math.tsqr_svd(dev(A))]
+    So = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(S - So).max() <= 1e-13 * So[0]
+    assert np.abs(U.T @ U - np.eye(40)).max() <= 1e-12
+    assert np.abs(V @ V.T - np.eye(40)).max() <= 1e-12
+    assert np.abs((U * S) @ V - A).max() <= 1e-12 * np.abs(A).max()
+    Z = np.zeros((300, 7))
+    U, S, V = [host(t) for t in pl.math.tsqr_svd(dev(Z))]
+    assert np.all(S == 0) and np.abs(V @ V.T - np.eye(7)).max() <= 1e-14 and np.abs(U.T @ U - np.eye(7)).max() <= 1e-14
+
+
 def test_error_behaviour(pl):
     with pytest.raises(ValueError, match="at least n rows"):
         pl.math.tsqr_svd(dev(np.zeros((3, 5))))

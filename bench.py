@@ -41,6 +41,15 @@ def f_alg(m, n):
     return 4.0 * m * n * n
 
 
+def workload_config(rows, n, size):
+    """The `config` object, identical for both arms."""
+    cfg_name = "BASELINE configs[1]" if (rows == ROWS_PER_GPU and n == N_COLS) else \
+               ("BASELINE configs[4] 'billionaire' when run on 8 GPUs" if (rows == 125_000_000 and n == 64) else "custom shape")
+    return {"workload": f"tsqr_svd of synthetic {rows}x{n} fp64 per GPU ({cfg_name}; global {rows * size}x{n}, rows sharded)",
+            "rows_per_gpu": rows, "cols": n, "seed": SEED, "l2": f"inputs ({rows * n * 8 / 1e9:.1f} GB/GPU) larger than L2",
+            "f_alg": "4*m*n^2"}
+
+
 # ----------------------------------------------------------------------------------------------
 # synthetic data (same formulas as oracle/synth.py, evaluated on the device in row chunks)
 # ----------------------------------------------------------------------------------------------
@@ -160,8 +169,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "tsqr_svd_gflops", "value": cb["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"tsqr_svd {ROWS_PER_GPU}x{n} fp64 per GPU (BASELINE configs[1]); CPU arm times a bounded sample",
-                       "rows_per_gpu": args.rows, "cols": n},
+            "config": workload_config(args.rows, n, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -317,14 +325,10 @@ def run_ours(args):
         if size == 1 and not args.no_cpu:
             cb = cpu_reference(args.cpu_rows, n, 1, 0)
         value = f_alg(m_global, n) / (ms * 1e-3) * 1e-9
-        cfg_name = "BASELINE configs[1]" if (args.rows == ROWS_PER_GPU and n == N_COLS) else \
-                   ("BASELINE configs[4] 'billionaire' when run on 8 GPUs" if (args.rows == 125_000_000 and n == 64) else "custom shape")
         line = {"metric": "tsqr_svd_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"tsqr_svd of synthetic {args.rows}x{n} fp64 per GPU ({cfg_name}; global {m_global}x{n}, rows sharded)",
-                           "rows_per_gpu": args.rows, "cols": n, "seed": SEED, "l2": f"inputs ({args.rows * n * 8 / 1e9:.1f} GB/GPU) larger than L2",
-                           "f_alg": "4*m*n^2"},
+                "config": workload_config(args.rows, n, size),
                 "rows_snapshots_per_s": m_global * n / (ms * 1e-3),
                 "frac_of_fp64_roofline": value * 1e-3 / (PEAK_FP64_TFLOPS * size),
                 "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "phases_ms": phases,

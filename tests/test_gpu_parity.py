@@ -299,3 +299,24 @@ def test_two_gpu_nccl_parity():
                         "--master-addr", "127.0.0.1", "--master-port", str(port), script],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_shape_fuzz(pl):
+    """Random (m, n) including tile / block / panel boundary cases: invariants against numpy."""
+    rng = np.random.default_rng(123)
+    shapes = [(32, 32), (33, 32), (127, 32), (128, 32), (129, 33), (160, 64), (161, 65), (4096, 96), (4097, 97),
+              (512 * 13 + 5, 40), (65, 65), (1024, 1), (2, 2), (1, 1)]
+    for _ in range(14):
+        n = int(rng.integers(1, 200))
+        m = int(n + rng.integers(0, 40000))
+        shapes.append((m, n))
+    for (m, n) in shapes:
+        A = rng.standard_normal((m, n)) * np.exp(rng.uniform(-3, 3, size=(1, n)))
+        U, S, V = [host(t) for t in pl.math.tsqr_svd(dev(A))]
+        So = np.linalg.svd(A, compute_uv=False)
+        assert np.abs(S - So).max() <= 1e-12 * So[0], (m, n)
+        assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12, (m, n)
+        assert np.abs(V @ V.T - np.eye(n)).max() <= 1e-12, (m, n)
+        assert np.abs((U * S) @ V - A).max() <= 1e-11 * np.abs(A).max(), (m, n)
+        mean = host(pl.math.temporal_mean(dev(A)))
+        assert np.abs(mean - A.mean(1)).max() <= 1e-13 * np.abs(A).max()

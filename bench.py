@@ -274,7 +274,7 @@ def run_ours(args):
                 "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/r01_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry",
                 "avg_launch_ms": upd_ms / max(upd_launch, 1), "launches_per_step": upd_launch,
                 "share_of_step": upd_ms / sum(msb), "traffic": None,
-                "ncu_traffic": {"launch": "first factor-pass launch of the 1,000,000 x 512 probe (15 chunks x 977 strips), profiles/r01_ncu_update_v2.txt",
+                "ncu_traffic": {"launch": "first factor-pass launch of the 1,000,000 x 512 probe (15 chunks x 977 strips), profiles/r01_ncu_update.txt",
                                 "dram_bytes": 7.948e9, "algorithmic_bytes": 7.94e9}}
 
     # ---- e2e through the host-pointer C ABI (rank 0 of N; every rank does its own shard)

@@ -506,10 +506,12 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       double acc[G][4];
 #pragma unroll
       for (int q = 0; q < G; q++) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+      const int qn = A.virt ? (first ? 1 : 0) : G;   // virtual-zero input: only the carried block (slab 0 of the first tile) contributes
 #pragma unroll
       for (int kk = 0; kk < 2; kk++) {
 #pragma unroll
         for (int q = 0; q < G; q++) {
+          if (q >= qn) continue;
           const double (*Cq)[SP] = (q == 0) ? C0 : S.Cs[q];
           double fa[8], fb[4];
 #pragma unroll

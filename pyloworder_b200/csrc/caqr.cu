@@ -679,33 +679,59 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   return 0;
 }
 
+static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb, double* Tws, double* Vup, double* Vpiv,
+                        cudaStream_t st) {
+  const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
+  ProfScope ps(PROF_PANEL, st);
+  static const int occ = getenv("PL_PANEL_OCC") ? atoi(getenv("PL_PANEL_OCC")) : 3;
+  double* Tl = Tws + L.t_off * (NB * NB);
+  double* Vl = li > 0 ? Vup + L.v_off * (TB * NB) : nullptr;
+  double* Pl = li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB);
+  if (occ == 4)
+    caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+  else if (occ == 2)
+    caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+  else
+    caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
+// Factorisation driver.  Per panel: the panel kernels of the tree levels above level 0 (tiny, latency bound) depend only
+// on the level-0 PANEL kernel, so they run on a side stream while the main stream applies the level-0 reflectors to the
+// trailing columns; the upper-level updates follow on the main stream.
 int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st) {
+  static const bool two_streams = getenv("PL_NO_STREAMS") == nullptr;
+  static cudaStream_t ss = nullptr;
+  static cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (two_streams && !ss) {
+    int lo = 0, hi = 0;
+    PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PL_CUDA(cudaStreamCreateWithPriority(&ss, cudaStreamNonBlocking, hi));
+    PL_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+  }
   for (int p = 0; p < P.K; p++) {
-    const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
+    const int col0 = p * NB;
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
-    for (size_t li = 0; li < P.panels[p].size(); li++) {
+    const int nl = (int)P.panels[p].size();
+    const bool split = two_streams && nl > 1 && ntrail > 0 && P.panels[p][0].ntiles >= 4096;
+    int rc = launch_panel(P, p, P.panels[p][0], 0, Vb, Tws, Vup, Vpiv, st);
+    if (rc) return rc;
+    if (split) {
+      PL_CUDA(cudaEventRecord(e0, st));
+      PL_CUDA(cudaStreamWaitEvent(ss, e0, 0));
+      for (int li = 1; li < nl; li++)
+        if ((rc = launch_panel(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, ss))) return rc;
+      PL_CUDA(cudaEventRecord(e1, ss));
+    }
+    rc = launch_update(P, p, P.panels[p][0], 0, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
+    if (rc) return rc;
+    if (split) PL_CUDA(cudaStreamWaitEvent(st, e1, 0));
+    for (int li = 1; li < nl; li++) {
       const Level& L = P.panels[p][li];
-      {
-        ProfScope ps(PROF_PANEL, st);
-        static const int occ = getenv("PL_PANEL_OCC") ? atoi(getenv("PL_PANEL_OCC")) : 3;
-        if (occ == 4)
-          caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
-                                                                  li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
-                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
-        else if (occ == 2)
-          caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
-                                                                  li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
-                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
-        else
-          caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s,
-                                                                  li > 0, Tws + L.t_off * (NB * NB),
-                                                                  li > 0 ? Vup + L.v_off * (TB * NB) : nullptr,
-                                                                  li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB));
-      }
-      PL_LAUNCH_CHECK();
-      int rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
+      if (!split && (rc = launch_panel(P, p, L, li, Vb, Tws, Vup, Vpiv, st))) return rc;
+      rc = launch_update(P, p, L, li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
       if (rc) return rc;
     }
   }

@@ -274,11 +274,13 @@ def run_ours(args):
                 "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/r01_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry",
                 "avg_launch_ms": upd_ms / max(upd_launch, 1), "launches_per_step": upd_launch,
                 "share_of_step": upd_ms / sum(msb), "traffic": None,
+                "timing": "CUDA events around every launch of one extra step",
                 "ncu_traffic": {"launch": "first factor-pass launch of the 1,000,000 x 512 probe (15 chunks x 977 strips), profiles/r01_ncu_update.txt",
                                 "dram_bytes": 7.948e9, "algorithmic_bytes": 7.94e9}}
 
     # ---- e2e through the host-pointer C ABI (rank 0 of N; every rank does its own shard)
     e2e = None
+    S_dev = S.cpu() if size == 1 else None
     del S, V
     # host memory: 2 pinned buffers of m_e2e x n per rank; with several ranks on one node the e2e sample is capped
     e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else 1_000_000)
@@ -315,8 +317,10 @@ def run_ours(args):
         e2e = {"value": f_alg(m_e2e * size, n) / dt * 1e-9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": m_e2e * n * 8, "d2h_bytes_per_step": m_e2e * n * 8 + n * 8 + n * n * 8,
                "rows_per_gpu": m_e2e, "ms_per_step": dt * 1e3,
-               "path": "pl_tsqr_svd_host_f64 (host pointers; chunked H2D + compute + chunked D2H inside the timed region, device buffers cached by the library after the warm-up call)" if size == 1
+               "path": "pl_tsqr_svd_host_f64 (host pointers; row-chunk pipeline H2D || factor+Q, GEMM || D2H inside the timed region, device buffers cached by the library after the warm-up call)" if size == 1
                        else "pyloworder_b200.math.tsqr_svd on pinned host tensors (H2D + compute + D2H inside the timed region)"}
+        if size == 1 and m_e2e == m:
+            e2e["s_rel_diff_vs_device_path"] = float((host_S - S_dev).abs().max() / S_dev[0])
     except Exception as ex:  # host memory too small etc.
         e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
 

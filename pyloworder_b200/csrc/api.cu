@@ -349,9 +349,10 @@ int pl_reconstruct_f64(double* X, const double* U, int64_t ldu, const double* S,
   return gemm_tall(X, n, U, ldu, (double*)ws, np, m, n, N, st);
 }
 
-// Device buffers of the host-pointer entry point are cached across calls (grow-only): a 100 GB cudaMalloc /
+// Device buffers of the host-pointer entry point are cached across calls (grow-only): a multi-GB cudaMalloc /
 // cudaFree pair per call costs several hundred milliseconds.  pl_host_cache_free() releases them.
-static struct HostCache { void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t cap[5] = {0, 0, 0, 0, 0}; } g_hc;
+constexpr int HC_SLOTS = 6;
+static struct HostCache { void* p[HC_SLOTS] = {}; size_t cap[HC_SLOTS] = {}; } g_hc;
 static int hc_get(int slot, size_t bytes, void** out) {
   if (g_hc.cap[slot] < bytes) {
     if (g_hc.p[slot]) cudaFree(g_hc.p[slot]);
@@ -364,61 +365,144 @@ static int hc_get(int slot, size_t bytes, void** out) {
   return 0;
 }
 void pl_host_cache_free(void) {
-  for (int i = 0; i < 5; i++) { if (g_hc.p[i]) cudaFree(g_hc.p[i]); g_hc.p[i] = nullptr; g_hc.cap[i] = 0; }
+  for (int i = 0; i < HC_SLOTS; i++) { if (g_hc.p[i]) cudaFree(g_hc.p[i]); g_hc.p[i] = nullptr; g_hc.cap[i] = 0; }
 }
 
+// Row-chunk count of the host pipeline: ~2 GiB of snapshots per chunk, at least 4 chunks above 512 MiB, and every
+// chunk at least 4n rows tall (PL_HOST_CHUNKS overrides).
+static int host_chunks(int64_t m, int64_t n) {
+  const double bytes = (double)m * n * 8;
+  int64_t c = (int64_t)ceil(bytes / 2147483648.0);
+  if (bytes > 536870912.0 && c < 4) c = 4;
+  if (const char* e = getenv("PL_HOST_CHUNKS")) c = atoi(e);
+  if (c > 64) c = 64;
+  while (c > 1 && m / c < 4 * n) c--;
+  return c < 1 ? 1 : (int)c;
+}
+
+// Host-pointer TSQR-SVD (replaces dtsqr_svd, pyLOM/vmmath/src/svd.c:~1390, for one rank).  The rows are processed as
+// C chunks, i.e. as a two-level TSQR on one device, so that PCIe and the GPU work at the same time:
+//   H2D(c+1)            ||  factor(c), R_c, explicit Q_c            (copy stream / compute stream)
+//   QR of the stacked R_c, Jacobi SVD, B = Q_stack Ur               (side stream, next to the last chunk's Q_c)
+//   U_c = Q_c B_c (GEMM) ||  D2H(c-1)                               (ping-pong output buffers)
 int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
   PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
-  const size_t ab = (size_t)m * n * 8, wsb = pl_qr_workspace_bytes(m, n);
-  void *dA = nullptr, *dU = nullptr, *dS = nullptr, *dV = nullptr, *ws = nullptr;
-  int rc;
-  if ((rc = hc_get(0, ab, &dA)) || (rc = hc_get(1, ab, &dU)) || (rc = hc_get(2, (size_t)n * 8, &dS)) ||
-      (rc = hc_get(3, (size_t)n * n * 8, &dV)) || (rc = hc_get(4, wsb, &ws))) { pl_host_cache_free(); return rc; }
-  static cudaStream_t st = nullptr, cs = nullptr;          // compute / copy streams of the host entry point
-  if (!st) { PL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); PL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)); }
-  WsLayout L = make_layout(m, n);
-  const Plan& P = L.plan;
-  // ---- H2D in row chunks on the copy stream; the padding copy of a chunk starts as soon as it has landed
-  const int NCH = 8;
-  cudaEvent_t ev[NCH];
-  for (int c = 0; c < NCH; c++) PL_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
-  double* Vb = at(ws, L.vb);
-  for (int c = 0; c < NCH; c++) {
-    const int64_t r0 = m * c / NCH, r1 = m * (c + 1) / NCH;
-    if (r1 <= r0) continue;
-    PL_CUDA(cudaMemcpyAsync((double*)dA + r0 * n, Ai + r0 * n, (size_t)(r1 - r0) * n * 8, cudaMemcpyHostToDevice, cs));
-    PL_CUDA(cudaEventRecord(ev[c], cs));
-    PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
-    rc = copy_pad(Vb + r0 * P.npad, P.npad, (const double*)dA + r0 * n, n, r1 - r0, n, P.npad, st);
-    if (rc) return rc;
+  int C = host_chunks(m, n);
+  const int64_t npad = round_up(n, NB);
+  const bool direct = (npad == n);                       // rows land in the factorisation buffer as they are
+  int64_t mc = round_up((m + C - 1) / C, TB);            // whole tiles per chunk; the last chunk takes the remainder
+  C = (int)((m + mc - 1) / mc);
+  if (C > 1 && m - (int64_t)(C - 1) * mc < 4 * n) C--;   // ... and absorbs a remainder that would be too short
+  if (C == 1) mc = m;
+  struct Chunk { int64_t r0, rows; Plan P; size_t vb, tws, vup, vpiv; };
+  std::vector<Chunk> ch(C);
+  size_t vb_bytes = 0, aux_bytes = 0;
+  int64_t max_rows = 0;
+  for (int c = 0; c < C; c++) {
+    Chunk& k = ch[c];
+    k.r0 = (int64_t)c * mc; k.rows = (c == C - 1) ? m - k.r0 : mc;
+    if (k.rows < n) { set_error("host pipeline: chunk %d has %lld rows < n", c, (long long)k.rows); return -5; }
+    k.P = make_plan(k.rows, n);
+    k.vb = vb_bytes;   vb_bytes += al((size_t)k.P.mrows * k.P.npad * 8);
+    k.tws = aux_bytes;  aux_bytes += al((size_t)k.P.t_tiles * NB * NB * 8);
+    k.vup = aux_bytes;  aux_bytes += al((size_t)(k.P.vup_tiles > 0 ? k.P.vup_tiles : 1) * TB * NB * 8);
+    k.vpiv = aux_bytes; aux_bytes += al((size_t)k.P.vpiv_strips * NB * NB * 8);
+    if (k.rows > max_rows) max_rows = k.rows;
   }
-  PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
-  // ---- factor, small SVD, explicit Q (all on the compute stream)
-  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
-  if (rc) return rc;
-  double* R = at(ws, L.r);
-  double* Ur = at(ws, L.ur);
-  if ((rc = caqr_extract_r(P, Vb, R, n, st))) return rc;
-  if ((rc = svd_small(Ur, n, (double*)dS, (double*)dV, n, R, n, n, at(ws, L.svd), nullptr, st))) return rc;
-  if ((rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st))) return rc;
+  // small buffers: stacked R (C n x n), B = Q_stack Ur (C n x n), R2, Ur, packed B chunk, Jacobi scratch, level-2 workspace
   const int64_t kp = round_up(n, 16), np = round_up(n, 64);
-  double* Bp = at(ws, L.bp);
-  if ((rc = pad_small(Bp, kp, np, Ur, n, n, n, nullptr, st))) return rc;
-  // ---- back-multiply in row chunks; the D2H of a chunk overlaps the GEMM of the next one
-  for (int c = 0; c < NCH; c++) {
-    const int64_t r0 = m * c / NCH, r1 = m * (c + 1) / NCH;
-    if (r1 <= r0) continue;
-    rc = gemm_tall((double*)dU + r0 * n, n, Vb + r0 * P.npad, P.npad, Bp, np, r1 - r0, n, kp, st);
-    if (rc) return rc;
+  const int64_t m2 = (int64_t)C * n;
+  WsLayout L2 = make_layout(m2, n);
+  size_t off = aux_bytes;
+  const size_t o_rs = off;  off += al((size_t)m2 * n * 8);
+  const size_t o_bs = off;  off += al((size_t)m2 * n * 8);
+  const size_t o_r2 = off;  off += al((size_t)n * n * 8);
+  const size_t o_ur = off;  off += al((size_t)n * n * 8);
+  const size_t o_bp = off;  off += al((size_t)kp * np * 8);
+  const size_t o_svd = off; off += al((size_t)svd_small_scratch_doubles(n) * 8);
+  const size_t o_ws2 = off; off += C > 1 ? L2.total : 0;
+  void *dVb = nullptr, *dOut = nullptr, *dS = nullptr, *dV = nullptr, *aux = nullptr, *stage = nullptr;
+  const size_t chunk_out = al((size_t)max_rows * n * 8);
+  int rc;
+  if ((rc = hc_get(0, vb_bytes, &dVb)) || (rc = hc_get(1, 2 * chunk_out, &dOut)) || (rc = hc_get(2, (size_t)n * 8, &dS)) ||
+      (rc = hc_get(3, (size_t)n * n * 8, &dV)) || (rc = hc_get(4, off, &aux)) ||
+      (!direct && (rc = hc_get(5, 2 * chunk_out, &stage)))) { pl_host_cache_free(); return rc; }
+  static cudaStream_t st = nullptr, cs = nullptr, s2 = nullptr;   // compute / copy / small-factor streams
+  static cudaEvent_t eR = nullptr, eB = nullptr;
+  if (!st) {
+    int lo = 0, hi = 0;
+    PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    PL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    PL_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
+    PL_CUDA(cudaEventCreateWithFlags(&eR, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&eB, cudaEventDisableTiming));
+  }
+  std::vector<cudaEvent_t> ev(C), evs(2), evd(2);
+  for (auto* v : {&ev, &evs, &evd}) for (auto& e : *v) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  struct EvGuard { std::vector<cudaEvent_t>*a, *b, *c; ~EvGuard() { for (auto* v : {a, b, c}) for (auto e : *v) cudaEventDestroy(e); } }
+      guard{&ev, &evs, &evd};
+  double* Rs = at(aux, o_rs);
+  double* Bs = at(aux, o_bs);
+  double* R2 = at(aux, o_r2);
+  double* Ur = at(aux, o_ur);
+  double* Bp = at(aux, o_bp);
+  // ---- phase 1: chunks arrive, get factored and turned into explicit Q_c while the next chunk is on the wire
+  for (int c = 0; c < C; c++) {
+    Chunk& k = ch[c];
+    double* Vb = at(dVb, k.vb);
+    const size_t bytes = (size_t)k.rows * n * 8;
+    if (direct) {
+      PL_CUDA(cudaMemcpyAsync(Vb, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
+      PL_CUDA(cudaEventRecord(ev[c], cs));
+      PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+    } else {
+      double* sg = reinterpret_cast<double*>(static_cast<char*>(stage) + (size_t)(c & 1) * chunk_out);
+      if (c >= 2) PL_CUDA(cudaStreamWaitEvent(cs, evs[c & 1], 0));           // staging buffer consumed
+      PL_CUDA(cudaMemcpyAsync(sg, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
+      PL_CUDA(cudaEventRecord(ev[c], cs));
+      PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+      if ((rc = copy_pad(Vb, k.P.npad, sg, n, k.rows, n, k.P.npad, st))) return rc;
+      PL_CUDA(cudaEventRecord(evs[c & 1], st));
+    }
+    PL_CUDA(cudaMemsetAsync(Vb + (size_t)k.rows * k.P.npad, 0, (size_t)(k.P.mrows - k.rows) * k.P.npad * 8, st));
+    if ((rc = caqr_factor(k.P, Vb, at(aux, k.tws), at(aux, k.vup), at(aux, k.vpiv), st))) return rc;
+    if ((rc = caqr_extract_r(k.P, Vb, C > 1 ? Rs + (size_t)c * n * n : R2, n, st))) return rc;
+    if (c == C - 1) PL_CUDA(cudaEventRecord(eR, st));
+    if ((rc = caqr_form_q(k.P, Vb, at(aux, k.tws), at(aux, k.vup), at(aux, k.vpiv), st))) return rc;
+  }
+  // ---- phase 2 (side stream, beside the last chunk's Q formation): stacked-R QR, Jacobi SVD, B = Q_stack Ur
+  PL_CUDA(cudaStreamWaitEvent(s2, eR, 0));
+  const double* B = Ur;
+  if (C > 1) {
+    void* ws2 = static_cast<char*>(aux) + o_ws2;
+    if ((rc = qr_factor(R2, nullptr, Rs, m2, n, 0, ws2, L2, s2))) return rc;
+  }
+  if ((rc = svd_small(Ur, n, (double*)dS, (double*)dV, n, R2, n, n, at(aux, o_svd), nullptr, s2))) return rc;
+  if (C > 1) {
+    void* ws2 = static_cast<char*>(aux) + o_ws2;
+    if ((rc = qr_apply_q(Bs, n, Ur, n, n, m2, n, 0, ws2, L2, s2))) return rc;
+    B = Bs;
+  }
+  PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, s2));
+  PL_CUDA(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s2));
+  PL_CUDA(cudaEventRecord(eB, s2));
+  PL_CUDA(cudaStreamWaitEvent(st, eB, 0));
+  // ---- phase 3: U_c = Q_c B_c; the D2H of a chunk overlaps the GEMM of the next one
+  for (int c = 0; c < C; c++) {
+    Chunk& k = ch[c];
+    double* out = reinterpret_cast<double*>(static_cast<char*>(dOut) + (size_t)(c & 1) * chunk_out);
+    if (c >= 2) PL_CUDA(cudaStreamWaitEvent(st, evd[c & 1], 0));             // output buffer drained
+    if ((rc = pad_small(Bp, kp, np, B + (size_t)c * n * n, n, n, n, nullptr, st))) return rc;
+    if ((rc = gemm_tall(out, n, at(dVb, k.vb), k.P.npad, Bp, np, k.rows, n, kp, st))) return rc;
     PL_CUDA(cudaEventRecord(ev[c], st));
     PL_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
-    PL_CUDA(cudaMemcpyAsync(Ui + r0 * n, (double*)dU + r0 * n, (size_t)(r1 - r0) * n * 8, cudaMemcpyDeviceToHost, cs));
+    PL_CUDA(cudaMemcpyAsync(Ui + k.r0 * n, out, (size_t)k.rows * n * 8, cudaMemcpyDeviceToHost, cs));
+    PL_CUDA(cudaEventRecord(evd[c & 1], cs));
   }
-  PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  PL_CUDA(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
+  PL_CUDA(cudaStreamSynchronize(s2));
   PL_CUDA(cudaStreamSynchronize(st));
   PL_CUDA(cudaStreamSynchronize(cs));
-  for (int c = 0; c < NCH; c++) cudaEventDestroy(ev[c]);
   return 0;
 }
 

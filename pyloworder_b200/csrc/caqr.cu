@@ -697,43 +697,57 @@ static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb
   return 0;
 }
 
-// Factorisation driver.  Per panel: the panel kernels of the tree levels above level 0 (tiny, latency bound) depend only
-// on the level-0 PANEL kernel, so they run on a side stream while the main stream applies the level-0 reflectors to the
-// trailing columns; the upper-level updates follow on the main stream.
+// Factorisation driver.  Optional one-panel look-ahead on two streams (PL_LOOKAHEAD=1, read per call): panel p+1 is
+// factored on a high-priority side stream while the main stream is still applying panel p to the columns right of it:
+//   main:  U(p; columns of panel p+1)  -> E ->  U(p; remaining columns)              -> wait F -> next panel
+//   side:                         wait E ->  panel kernels of p+1, all tree levels -> F
+// (the panel kernels of the upper tree levels read only the pivot blocks written by the level below, so all levels of
+// a panel can run back to back before any of its updates).  Measured at 8 M x 512: no gain (622.5 vs 621.6 ms) --
+// two update CTAs fill the register file of an SM (2 x 256 x 128), so a panel CTA only ever replaces an update CTA
+// instead of running beside it.  Off by default; kept for a future update kernel with a smaller footprint.
 int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st) {
-  static const bool two_streams = getenv("PL_NO_STREAMS") == nullptr;
   static cudaStream_t ss = nullptr;
-  static cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (two_streams && !ss) {
+  static cudaEvent_t eE = nullptr, eF = nullptr;
+  const bool look = P.K > 1 && P.panels[0][0].ntiles >= 2048 && getenv("PL_LOOKAHEAD") != nullptr;
+  if (look && !ss) {
     int lo = 0, hi = 0;
     PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     PL_CUDA(cudaStreamCreateWithPriority(&ss, cudaStreamNonBlocking, hi));
-    PL_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-    PL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&eE, cudaEventDisableTiming));
+    PL_CUDA(cudaEventCreateWithFlags(&eF, cudaEventDisableTiming));
   }
-  for (int p = 0; p < P.K; p++) {
+  int rc;
+  if (!look) {
+    for (int p = 0; p < P.K; p++) {
+      const int col0 = p * NB;
+      const int ntrail = (int)((P.npad - col0 - NB) / NB);
+      for (size_t li = 0; li < P.panels[p].size(); li++) {
+        const Level& L = P.panels[p][li];
+        if ((rc = launch_panel(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, st))) return rc;
+        rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
+  for (size_t li = 0; li < P.panels[0].size(); li++)
+    if ((rc = launch_panel(P, 0, P.panels[0][li], (int)li, Vb, Tws, Vup, Vpiv, st))) return rc;
+  for (int p = 0; p + 1 < P.K; p++) {
     const int col0 = p * NB;
     const int ntrail = (int)((P.npad - col0 - NB) / NB);
     const int nl = (int)P.panels[p].size();
-    const bool split = two_streams && nl > 1 && ntrail > 0 && P.panels[p][0].ntiles >= 4096;
-    int rc = launch_panel(P, p, P.panels[p][0], 0, Vb, Tws, Vup, Vpiv, st);
-    if (rc) return rc;
-    if (split) {
-      PL_CUDA(cudaEventRecord(e0, st));
-      PL_CUDA(cudaStreamWaitEvent(ss, e0, 0));
-      for (int li = 1; li < nl; li++)
-        if ((rc = launch_panel(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, ss))) return rc;
-      PL_CUDA(cudaEventRecord(e1, ss));
-    }
-    rc = launch_update(P, p, P.panels[p][0], 0, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
-    if (rc) return rc;
-    if (split) PL_CUDA(cudaStreamWaitEvent(st, e1, 0));
-    for (int li = 1; li < nl; li++) {
-      const Level& L = P.panels[p][li];
-      if (!split && (rc = launch_panel(P, p, L, li, Vb, Tws, Vup, Vpiv, st))) return rc;
-      rc = launch_update(P, p, L, li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
-      if (rc) return rc;
-    }
+    for (int li = 0; li < nl; li++)      // columns of the next panel first
+      if ((rc = launch_update(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, 1, 1, st)))
+        return rc;
+    PL_CUDA(cudaEventRecord(eE, st));
+    PL_CUDA(cudaStreamWaitEvent(ss, eE, 0));
+    for (size_t li = 0; li < P.panels[p + 1].size(); li++)
+      if ((rc = launch_panel(P, p + 1, P.panels[p + 1][li], (int)li, Vb, Tws, Vup, Vpiv, ss))) return rc;
+    PL_CUDA(cudaEventRecord(eF, ss));
+    for (int li = 0; li < nl; li++)
+      if ((rc = launch_update(P, p, P.panels[p][li], li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + 2 * NB, ntrail - 1, 1, st)))
+        return rc;
+    PL_CUDA(cudaStreamWaitEvent(st, eF, 0));
   }
   return 0;
 }

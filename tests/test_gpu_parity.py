@@ -246,6 +246,23 @@ def test_c_abi_host_entry_point(pl):
         assert_svd_parity((U2, S2, V2), (U, S, V))
 
 
+@pytest.mark.parametrize("m,n,chunks", [(20000, 96, 3), (20000, 100, 5), (9001, 33, 7), (4000, 64, 64)])
+def test_c_abi_host_pipeline_chunked(pl, monkeypatch, m, n, chunks):
+    """The host entry point as a multi-chunk (two-level TSQR) pipeline: padded and unpadded widths, ragged last
+    chunk, more chunks requested than the 4n-rows rule allows."""
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    monkeypatch.setenv("PL_HOST_CHUNKS", str(chunks))
+    A = synth.snapshots(m, n, 21)
+    U = np.zeros((m, n)); S = np.zeros(n); V = np.zeros((n, n))
+    for _ in range(2):      # second call reuses the cached device buffers
+        rc = L.pl_tsqr_svd_host_f64(U.ctypes.data, S.ctypes.data, V.ctypes.data, A.ctypes.data, m, n)
+        assert rc == 0, L.pl_last_error()
+        assert_svd_parity(po.tsqr_svd(A), (U, S, V))
+        assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12
+    L.pl_host_cache_free()
+
+
 def test_large_properties(pl):
     """Size-independent properties at a size the CPU oracle would not finish quickly."""
     m, n = 2_000_000, 64

@@ -44,6 +44,13 @@ int pl_norm_variance_f64(double* out, const double* X, const double* X_mean, con
 size_t pl_matmul_workspace_bytes(int64_t n, int64_t k);
 int pl_matmul_f64(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                   int64_t m, int64_t n, int64_t k, void* ws, size_t ws_bytes, void* stream);
+/* rank-local part of dmatmulp(double *C, double *A, double *B, m, n, k) (vector_matrix.c:344-356: cblas_dgemm +
+ * MPI_Allreduce) for the shapes pyLOM calls it with -- matmulp(Ai.T, Qi), matmulp(Qi.T, Ai) in randomized_qr
+ * (vmmath/svd.py:139,143) and matmulp(U.T, Y) in DMD: C(a,b) = X^T Y with X (m,a), Y (m,b) row-major tall operands,
+ * i.e. a reduction over the distributed rows.  The caller adds C over the ranks (one all-reduce). */
+size_t pl_matmul_tn_workspace_bytes(int64_t a, int64_t b);
+int pl_matmul_tn_f64(double* C, int64_t ldc, const double* X, int64_t ldx, int64_t a, const double* Y, int64_t ldy,
+                     int64_t b, int64_t m, void* ws, size_t ws_bytes, void* stream);
 /* replaces dvecmat(double *v, double *A, m, n): C[i,:] = v[i] A[i,:] (out of place)  vector_matrix.c:401-414 */
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream);
 

@@ -126,9 +126,38 @@ def make_input(m, n, kind, seed):
     return synth.snapshots(m, n, seed)
 
 
+# randomized SVD (pyLOM/vmmath/svd.py:120-144,254-273): one rank only -- the reference seeds numpy's GLOBAL generator
+# (svd.py:131,264), which the simulated ranks (threads) would race on; multi-rank parity goes through the oracle.
+RSVD_CASES = [
+    # name, m, n, kind, seed(input), r, q, seed(sketch)
+    ("rsvd_synth_900x40", 900, 40, "synth", 2021, 8, 2, 7),
+    ("rsvd_rand_500x24", 500, 24, "rand", 5, 6, 3, 123),
+    ("rsvd_synth_1200x96_q0", 1200, 96, "synth", 2022, 12, 0, 99),
+]
+
+
+def main_rsvd(outdir):
+    for name, m, n, kind, seed, r, q, sk in RSVD_CASES:
+        A = make_input(m, n, kind, seed)
+        ref = _load_rank(_World(1), 0)
+        Q, B = ref.svd.randomized_qr(A, r, q, seed=sk)
+        U, S, V = ref.svd.randomized_svd(A, r, q, seed=sk)
+        Up, Sp, Vp = ref.POD.run(A, remove_mean=True, randomized=True, r=r, q=q, seed=sk)
+        np.random.seed(sk)
+        omega = np.random.rand(n, r)
+        blob = {"A": A, "r": np.array(r), "q": np.array(q), "seed": np.array(sk), "omega": omega,
+                "Q": Q, "B": B, "U": U, "S": S, "V": V, "pod_U": Up, "pod_S": Sp, "pod_V": Vp}
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, S[:3], os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     outdir = os.path.join(HERE, "..", "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    if "--rsvd" in sys.argv:           # only the randomized fixtures (leaves the others untouched)
+        return main_rsvd(outdir)
+    main_rsvd(outdir)
     for name, m, n, kind, seed, ranks in CASES:
         A = make_input(m, n, kind, seed)
         blob = {"A": A}

@@ -189,12 +189,56 @@ def tsqr_svd(A_list):
     return (U[0] if single else U), S, V
 
 
+def matmulp(A_list, B_list):
+    """C = sum over ranks of A_i x B_i (pyLOM/vmmath/maths.py:93-110; dmatmulp, src/vector_matrix.c:344-356:
+    local GEMM + MPI_Allreduce).  A_i (M, q_i), B_i (q_i, N): the inner dimension is the distributed one."""
+    tot = np.matmul(A_list[0], B_list[0])
+    for A, B in zip(A_list[1:], B_list[1:]):
+        tot = tot + np.matmul(A, B)
+    return tot
+
+
+def sketch_matrix(n: int, r: int, seed: int) -> np.ndarray:
+    """The Gaussian-free sketch of randomized_qr: ``np.random.seed(seed); np.random.rand(n, r)``
+    (pyLOM/vmmath/svd.py:131-133).  RandomState(seed) is the same MT19937 stream without touching the global state."""
+    return np.random.RandomState(seed).rand(n, r)
+
+
+def randomized_qr(A_list, r: int, q: int, seed: int):
+    """Randomized range finder with q power iterations on P simulated ranks (pyLOM/vmmath/svd.py:120-144;
+    drandomized_qr, src/svd.c:1267-1319).  Returns ([Q_i (m_i, r)], B (r, n))."""
+    single = isinstance(A_list, np.ndarray)
+    As = [A_list] if single else A_list
+    n = As[0].shape[1]
+    omega = sketch_matrix(n, r, seed)
+    Y = [matmul(A, omega) for A in As]
+    for _ in range(q):
+        Q, _R = tsqr(Y)
+        Q2 = matmulp([A.T for A in As], Q)
+        Y = [matmul(A, Q2) for A in As]
+    Q, _R = tsqr(Y)
+    B = matmulp([Qi.T for Qi in Q], As)
+    return (Q[0] if single else Q), B
+
+
+def randomized_svd(A_list, r: int, q: int, seed: int):
+    """Randomized SVD (pyLOM/vmmath/svd.py:254-273; drandomized_svd, src/svd.c:1453-1519):
+    ([U_i (m_i, r)], S (r), V (r, n))."""
+    single = isinstance(A_list, np.ndarray)
+    As = [A_list] if single else A_list
+    Q, B = randomized_qr(As, r, q, seed)
+    Ur, S, V = svd(B)
+    U = [matmul(Qi, Ur) for Qi in Q]
+    return (U[0] if single else U), S, V
+
+
 # --------------------------------------------------------------------------------------
 # POD
 # --------------------------------------------------------------------------------------
-def pod_run(X_list, remove_mean: bool = True, divide_variance: bool = False):
+def pod_run(X_list, remove_mean: bool = True, divide_variance: bool = False, randomized: bool = False, r: int = 1,
+            q: int = 3, seed: int = -1):
     """POD.run on P simulated ranks (pyLOM/POD/wrapper.py:16-51).  ``X_list`` may be a
-    single array.  randomized is outside the hot path."""
+    single array."""
     single = isinstance(X_list, np.ndarray)
     Xs = [X_list] if single else X_list
     if remove_mean and divide_variance:
@@ -203,7 +247,7 @@ def pod_run(X_list, remove_mean: bool = True, divide_variance: bool = False):
         Ys = [subtract_mean(X, temporal_mean(X)) for X in Xs]
     else:
         Ys = [X.copy() for X in Xs]
-    U, S, V = tsqr_svd(Ys)
+    U, S, V = randomized_svd(Ys, r, q, seed) if randomized else tsqr_svd(Ys)
     return (U[0] if single else U), S, V
 
 

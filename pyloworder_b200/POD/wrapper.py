@@ -4,9 +4,9 @@ import torch
 
 from .. import _lib, _dev
 from ..utils.cr import cr, cr_start, cr_stop
-from ..vmmath.svd import _tsqr_svd_dev
+from ..vmmath.svd import _tsqr_svd_dev, randomized_svd
 from ..vmmath.truncation import compute_truncation_residual
-from ..vmmath.averaging import temporal_mean, temporal_variance, norm_variance
+from ..vmmath.averaging import temporal_mean, subtract_mean, temporal_variance, norm_variance
 
 
 @cr('POD.run')
@@ -15,21 +15,25 @@ def run(X, remove_mean=True, divide_variance=False, randomized=False, r=1, q=3, 
 
     Returns U (m_i, n) spatial modes, S (n) singular values, V (n, n) = V^T temporal coefficients.
     X is not modified.  The centering (temporal_mean + subtract_mean, POD/wrapper.py:33-41) is fused
-    into the copy that feeds the factorisation.  `randomized` is outside the B200 hot path
-     and raises NotImplementedError.
+    into the copy that feeds the factorisation.  With randomized=True the r leading modes come from
+    randomized_svd (q power iterations, sketch seeded with `seed`): U (m_i, r), S (r), V (r, n).
     """
-    if randomized:
-        raise NotImplementedError("POD.run(randomized=True) is not part of the B200 hot path yet")
     Xd, kind = _dev.to_device(X, "X")
     center = bool(remove_mean)
-    if remove_mean and divide_variance:      # POD/wrapper.py:36-38 (only effective together with remove_mean)
+    if remove_mean and (divide_variance or randomized):
         cr_start('POD.temporal_mean', 0)
         X_mean = temporal_mean(Xd)
-        Xd = norm_variance(Xd, X_mean, temporal_variance(Xd, X_mean))
+        if divide_variance:                  # POD/wrapper.py:36-38 (only effective together with remove_mean)
+            Xd = norm_variance(Xd, X_mean, temporal_variance(Xd, X_mean))
+        else:                                # the randomized path reads Y several times: materialise it once
+            Xd = subtract_mean(Xd, X_mean)
         cr_stop('POD.temporal_mean', 0)
         center = False
     cr_start('POD.SVD', 0)
-    U, S, V, _ = _tsqr_svd_dev(Xd, center=center)
+    if randomized:
+        U, S, V = randomized_svd(Xd, r, q, seed=seed)
+    else:
+        U, S, V, _ = _tsqr_svd_dev(Xd, center=center)
     cr_stop('POD.SVD', 0)
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(V, kind)
 

@@ -23,6 +23,8 @@ _SIGS = {
     "pl_qr_factor_var_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
     "pl_matmul_workspace_bytes": (_sz, [_i64, _i64]),
     "pl_matmul_f64": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "pl_matmul_tn_workspace_bytes": (_sz, [_i64, _i64]),
+    "pl_matmul_tn_f64": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "pl_vecmat_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pl_rmse_workspace_bytes": (_sz, []),
     "pl_rmse_sums_f64": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),

@@ -168,6 +168,19 @@ int pl_norm_variance_f64(double* out, const double* X, const double* X_mean, con
   PL_ARG(m >= 0 && n > 0, 5, "m >= 0, n > 0");
   return norm_variance(out, n, X, X_mean, X_var, m, n, n, (cudaStream_t)stream);
 }
+size_t pl_matmul_tn_workspace_bytes(int64_t a, int64_t b) { return (a > 0 && b > 0) ? gemm_tn_workspace_bytes(a, b) : 256; }
+int pl_matmul_tn_f64(double* C, int64_t ldc, const double* X, int64_t ldx, int64_t a, const double* Y, int64_t ldy, int64_t b,
+                     int64_t m, void* ws, size_t ws_bytes, void* stream) {
+  PL_ARG(a >= 0 && b >= 0 && m >= 0, 5, "negative size");
+  if (a == 0 || b == 0) return 0;
+  PL_ARG(C && ldc >= b, 2, "C / ldc");
+  PL_ARG(m == 0 || (X && ldx >= a), 4, "X / ldx");
+  PL_ARG(m == 0 || (Y && ldy >= b), 7, "Y / ldy");
+  if (!ws || ws_bytes < gemm_tn_workspace_bytes(a, b) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("matmul_tn: workspace too small or misaligned (need %zu bytes)", gemm_tn_workspace_bytes(a, b)); return -10;
+  }
+  return gemm_tn(C, ldc, X, ldx, a, Y, ldy, b, m, static_cast<double*>(ws), (cudaStream_t)stream);
+}
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream) {
   return vecmat(C, n, v, A, n, m, n, (cudaStream_t)stream);
 }

@@ -43,6 +43,10 @@ constexpr int SUMSQ_SCRATCH_DOUBLES = 2 * 148 * 4;
 
 // gemm.cu :  C[m x n] (ldc) = A[m x k] (lda) * Bp[kp x np] (ldb = np), Bp zero padded to kp%16==0, np%64==0
 int gemm_tall(double* C, int64_t ldc, const double* A, int64_t lda, const double* Bp, int64_t ldb, int64_t m, int64_t n, int64_t k, cudaStream_t st);
+// gemm_tn.cu : C (a x b, ldc) = X^T Y, X (m x a, ldx), Y (m x b, ldy); ws >= gemm_tn_workspace_bytes(a, b)
+size_t gemm_tn_workspace_bytes(int64_t a, int64_t b);
+int gemm_tn(double* C, int64_t ldc, const double* X, int64_t ldx, int64_t a, const double* Y, int64_t ldy, int64_t b, int64_t m,
+            double* ws, cudaStream_t st);
 int pad_small(double* dst, int64_t rows_p, int64_t cols_p, const double* src, int64_t lds, int64_t rows, int64_t cols, const double* rowscale, cudaStream_t st);
 
 // svd_small.cu : R (n x n, ldr) = Ur diag(S) VT ; Ur, VT n x n with given ld; scratch >= 2*n*n + 4*n + 64 doubles

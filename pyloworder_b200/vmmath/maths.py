@@ -43,11 +43,46 @@ def matmul(A, B):
     return _dev.from_device(C, kind)
 
 
+def _tall_transposed(A, what):
+    """A is (M, Q) with Q the long, row-distributed dimension (callers pass `Ai.T` / `Qi.T`).  Return the row-major
+    (Q, M) operand the kernel reads, without materialising a transposed copy when A is already a `.T` view."""
+    if isinstance(A, torch.Tensor) and A.is_cuda:
+        if A.dtype != torch.float64:
+            raise NotImplementedError(f"{what}: only float64 is implemented on the B200 path (got {A.dtype})")
+        if A.dim() != 2:
+            raise ValueError("expected a 2-D array")
+        return A.T, "torch"            # _strided2d() below copies only if the rows of A.T are not contiguous
+    if hasattr(A, "T") and not hasattr(A, "__cuda_array_interface__"):
+        return _dev.to_device(A.T, what)          # numpy / CPU torch: uploads A.T (no host copy for a .T view)
+    t, kind = _dev.to_device(A, what)
+    return t.T, kind
+
+
+def matmul_tn(X, Y):
+    """C(a, b) = X^T Y for two row-major tall device operands X (m, a), Y (m, b): the rank-local part of matmulp
+    (transposed-tall DMMA GEMM, reduction over the rows)."""
+    X, ldx = _strided2d(X)
+    Y, ldy = _strided2d(Y)
+    m, a = X.shape
+    m2, b = Y.shape
+    if m != m2:
+        raise ValueError(f"matmulp: inner dimensions differ ({m} vs {m2})")
+    C = torch.empty((a, b), dtype=torch.float64, device=X.device)
+    L = _lib.lib()
+    _, wp, wb = _dev.workspace(L.pl_matmul_tn_workspace_bytes(a, b), "matmul_tn", X.device)
+    _lib.check(L.pl_matmul_tn_f64(C.data_ptr(), b, X.data_ptr(), ldx, a, Y.data_ptr(), ldy, b, m, wp, wb, _dev.stream()),
+               "matmul_tn")
+    return C
+
+
 @cr('math.matmulp')
 def matmulp(A, B):
-    """C = A x B with the result summed over ranks (rows of B / columns of A are distributed)."""
-    Ad, kind = _to_dev_keep_view(A, "A")
-    C = matmul(Ad, _to_dev_keep_view(B, "B")[0])
+    """C(M,N) = A(M,Q) x B(Q,N) with Q the row-distributed dimension; the result is summed over the ranks and is the
+    same on all of them (pyLOM/vmmath/maths.py:93-110).  pyLOM calls it as matmulp(Ai.T, Qi) / matmulp(Qi.T, Ai):
+    both operands are tall row-major arrays and the product is a reduction over their rows."""
+    X, kind = _tall_transposed(A, "A")
+    Bd, _ = _to_dev_keep_view(B, "B")
+    C = matmul_tn(X, Bd)
     return _dev.from_device(mpi_reduce(C, op='sum', all=True), kind)
 
 

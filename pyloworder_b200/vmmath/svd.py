@@ -12,6 +12,7 @@ TSQR is valid for any reduction tree (Demmel et al. 2012, the paper svd.py:58 ci
 all-gather tree gives the same R up to row signs.  S and VT are identical on all ranks.
 """
 import os
+import time
 
 import torch
 
@@ -188,12 +189,74 @@ def qr(A):
     return _dev.from_device(Q, kind), _dev.from_device(R, kind)
 
 
+def _svd_dev(Ad):
+    """Thin SVD of a local device matrix of any shape: square -> Jacobi kernel; tall -> the single-rank TSQR-SVD;
+    wide (r x n, the B of randomized_svd) -> TSQR-SVD of the transpose with the factors swapped back."""
+    if Ad.dim() != 2:
+        raise ValueError("expected a 2-D array")
+    m, n = Ad.shape
+    if m == n:
+        return _engine.svd(Ad.contiguous())
+    if m > n:
+        U, S, VT, _ = _engine.tsqr_svd_single(Ad.contiguous())
+        return U, S, VT
+    Ut, S, VTt, _ = _engine.tsqr_svd_single(Ad.T.contiguous())        # A^T = Ut S VTt  =>  A = VTt^T S Ut^T
+    return VTt.T.contiguous(), S, Ut.T.contiguous()
+
+
 @cr('math.svd')
 def svd(A, method='gesdd'):
-    """Thin SVD of a small square matrix (the n x n R of this path): U, S (descending), V^T
-    (pyLOM/vmmath/svd.py:38-47).  `method` is accepted for signature compatibility."""
+    """Thin SVD of a local (not distributed) matrix: U (m,k), S (k, descending), V^T (k,n), k = min(m,n)
+    (pyLOM/vmmath/svd.py:38-47, dsvd src/svd.c:83-139).  `method` is accepted for signature compatibility."""
     Ad, kind = _dev.to_device(A, "A")
-    if Ad.dim() != 2 or Ad.shape[0] != Ad.shape[1]:
-        raise NotImplementedError("svd: only the square n x n case of the TSQR path is implemented; use tsqr_svd for tall matrices")
-    U, S, VT = _engine.svd(Ad)
+    U, S, VT = _svd_dev(Ad)
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)
+
+
+def _sketch_matrix(n, r, seed, device):
+    """omega = rand(n, r) from numpy's MT19937 seeded with `seed`: the same numbers the reference draws with
+    `np.random.seed(seed); np.random.rand(n, r)` (pyLOM/vmmath/svd.py:131-133), generated on the host (n*r values)
+    without touching numpy's global generator."""
+    import numpy as np
+    return torch.from_numpy(np.random.RandomState(int(seed)).rand(int(n), int(r))).to(device)
+
+
+def _randomized_qr_dev(Ad, r, q, seed):
+    from .maths import matmul, matmulp
+    m, n = Ad.shape
+    r = int(r)
+    if not 1 <= r <= n:
+        raise ValueError(f"randomized_qr: need 1 <= r <= n (got r={r}, n={n})")
+    if m < r:
+        raise ValueError(f"every rank needs at least r rows (got m_i={m} < r={r})")
+    seed = int(time.time()) if seed < 0 else int(seed)
+    omega = _sketch_matrix(n, r, seed, Ad.device)
+    Yi = matmul(Ad, omega)
+    for _ in range(int(q)):                    # power iterations, re-orthonormalised each time
+        Qi, _R = tsqr(Yi)
+        Q2i = matmulp(Ad.T, Qi)
+        Yi = matmul(Ad, Q2i)
+    Qi, _R = tsqr(Yi)
+    B = matmulp(Qi.T, Ad)
+    return Qi, B
+
+
+@cr('math.randomized_qr')
+def randomized_qr(Ai, r, q, seed=-1):
+    """Randomized range finder (pyLOM/vmmath/svd.py:120-144; drandomized_qr src/svd.c:1267-1319):
+    Ai (m_i, n) -> Qi (m_i, r) orthonormal over all ranks, B (r, n) = Q^T A identical on all ranks."""
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    Qi, B = _randomized_qr_dev(Ad, r, q, seed)
+    return _dev.from_device(Qi, kind), _dev.from_device(B, kind)
+
+
+@cr('math.randomized_svd')
+def randomized_svd(Ai, r, q, seed=-1):
+    """Randomized SVD (pyLOM/vmmath/svd.py:254-273; drandomized_svd src/svd.c:1453-1519):
+    Ai (m_i, n) -> Ui (m_i, r), S (r), V (r, n) = V^T."""
+    from .maths import matmul
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    Qi, B = _randomized_qr_dev(Ad, r, q, seed)
+    Ur, S, V = _svd_dev(B)
+    Ui = matmul(Qi, Ur)
+    return _dev.from_device(Ui, kind), _dev.from_device(S, kind), _dev.from_device(V, kind)

@@ -11,7 +11,9 @@ import pod_oracle as po
 import synth
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("rsvd_")]
+RSVD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("rsvd_")]
 
 SIG_TOL = 1e-10
 MODE_TOL = 1 - 1e-8
@@ -218,8 +220,8 @@ def test_error_behaviour(pl):
         pl.math.tsqr_svd(dev(np.zeros((3, 5))))
     with pytest.raises(NotImplementedError):
         pl.math.tsqr_svd(torch.zeros((10, 2), dtype=torch.float32, device="cuda"))
-    with pytest.raises(NotImplementedError):
-        pl.POD.run(dev(np.ones((10, 2))), randomized=True)
+    with pytest.raises(ValueError, match="1 <= r <= n"):
+        pl.POD.run(dev(np.ones((10, 2))), randomized=True, r=3)
     from pyloworder_b200 import _lib
     L = _lib.lib()
     rc = L.pl_tsqr_svd_f64(None, None, None, None, 3, 5, None, 0, None)
@@ -261,6 +263,79 @@ def test_c_abi_host_pipeline_chunked(pl, monkeypatch, m, n, chunks):
         assert_svd_parity(po.tsqr_svd(A), (U, S, V))
         assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12
     L.pl_host_cache_free()
+
+
+@pytest.mark.parametrize("m,a,b", [(5000, 16, 64), (5000, 64, 16), (40000, 8, 512), (33333, 33, 151), (20000, 151, 151),
+                                    (3001, 24, 40), (70, 5, 9), (100000, 200, 96), (17, 64, 64), (250000, 12, 999)])
+def test_matmul_tn_kernel(pl, m, a, b):
+    """C = X^T Y (the rank-local part of matmulp) against torch's fp64 matmul: all three tile shapes, the swapped
+    (a > b) orientation, odd leading dimensions (8-byte loads) and row counts that are not a multiple of the stage."""
+    g = torch.Generator(device="cuda"); g.manual_seed(m + a)
+    X = torch.randn((m, a), dtype=torch.float64, device="cuda", generator=g)
+    Y = torch.randn((m, b), dtype=torch.float64, device="cuda", generator=g)
+    from pyloworder_b200.vmmath.maths import matmul_tn
+    C = matmul_tn(X, Y)
+    ref = X.T @ Y
+    tol = 1e-13 * m ** 0.5 * 8
+    assert float((C - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    C2 = matmul_tn(X, Y)
+    assert torch.equal(C, C2), "split-K reduction must be deterministic"
+    # the public call shape: matmulp(Ai.T, Qi) on a .T view, and on strided column views
+    C3 = pl.math.matmulp(X.T, Y)
+    assert torch.equal(C3, C)
+    if a >= 8 and b >= 8:
+        C4 = pl.math.matmulp(X[:, 1:a - 2].T, Y[:, 3:b - 1])
+        assert float((C4 - ref[1:a - 2, 3:b - 1]).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    Cn = pl.math.matmulp(host(X).T, host(Y))
+    assert isinstance(Cn, np.ndarray) and np.abs(Cn - host(ref)).max() <= tol * max(1.0, float(ref.abs().max()))
+
+
+def test_svd_rectangular(pl):
+    """svd() of the wide (r x n) matrix B of randomized_svd and of a local tall matrix, against LAPACK."""
+    rng = np.random.default_rng(3)
+    for shape in [(8, 40), (12, 96), (1, 7), (64, 65), (300, 20)]:
+        B = rng.standard_normal(shape)
+        U, S, V = [host(t) for t in pl.math.svd(dev(B))]
+        k = min(shape)
+        assert U.shape == (shape[0], k) and S.shape == (k,) and V.shape == (k, shape[1])
+        So = np.linalg.svd(B, compute_uv=False)
+        assert np.abs(S - So).max() <= 1e-13 * So[0]
+        assert np.abs((U * S) @ V - B).max() <= 1e-13 * So[0] * 4
+        assert np.abs(U.T @ U - np.eye(k)).max() <= 1e-13 and np.abs(V @ V.T - np.eye(k)).max() <= 1e-13
+
+
+@pytest.mark.parametrize("path", RSVD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_randomized_svd_against_reference_golden(pl, path):
+    """randomized_qr / randomized_svd / POD.run(randomized=True) against the reference's own Python output for the
+    same seed (the sketch matrix is bit-identical: numpy MT19937 on the host, as in pyLOM/vmmath/svd.py:131-133)."""
+    g = np.load(path)
+    A, r, q, sk = g["A"], int(g["r"]), int(g["q"]), int(g["seed"])
+    Ad = dev(A)
+    Q, B = [host(t) for t in pl.math.randomized_qr(Ad, r, q, seed=sk)]
+    assert Q.shape == (A.shape[0], r) and B.shape == (r, A.shape[1])
+    assert np.abs(Q.T @ Q - np.eye(r)).max() <= 1e-12
+    assert np.abs(Q.T @ A - B).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+    assert np.abs(g["Q"] @ (g["Q"].T @ Q) - Q).max() <= 1e-9              # same range as the reference's Q
+    U, S, V = [host(t) for t in pl.math.randomized_svd(Ad, r, q, seed=sk)]
+    assert U.shape == (A.shape[0], r) and S.shape == (r,) and V.shape == (r, A.shape[1])
+    assert_svd_parity((g["U"], g["S"], g["V"]), (U, S, V))
+    Up, Sp, Vp = [host(t) for t in pl.POD.run(Ad, remove_mean=True, randomized=True, r=r, q=q, seed=sk)]
+    assert torch.equal(Ad, dev(A)), "POD.run must not modify X"
+    assert_svd_parity((g["pod_U"], g["pod_S"], g["pod_V"]), (Up, Sp, Vp))
+    # numpy in -> numpy out
+    Un, Sn, Vn = pl.math.randomized_svd(A, r, q, seed=sk)
+    assert isinstance(Un, np.ndarray) and np.abs(Sn - S).max() <= 1e-12 * S[0]
+
+
+@pytest.mark.parametrize("m,n,r,q", [(200000, 128, 16, 2), (60000, 512, 40, 1), (30000, 151, 10, 3)])
+def test_randomized_svd_against_oracle(pl, m, n, r, q):
+    A = synth.snapshots(m, n, 31)
+    ref = po.randomized_svd(A, r, q, 5)
+    got = [host(t) for t in pl.math.randomized_svd(dev(A), r, q, seed=5)]
+    assert_svd_parity(ref, got)
+    # the leading modes approximate the deterministic ones
+    S_full = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(got[1][:4] - S_full[:4]).max() <= 1e-6 * S_full[0]
 
 
 def test_large_properties(pl):

@@ -54,6 +54,8 @@ def test_truncation_rule_matches_golden(golden_dir):
     from pyloworder_b200.vmmath import compute_truncation_residual
     import glob
     for path in glob.glob(os.path.join(golden_dir, "*.npz")):
+        if os.path.basename(path).startswith("rsvd_"):
+            continue
         g = np.load(path)
         S = g["tsqr_svd_P1_S"]
         for r, N in zip(g["trunc_r"], g["trunc_N"]):

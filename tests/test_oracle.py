@@ -8,7 +8,9 @@ import pytest
 import pod_oracle as po
 import synth
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("rsvd_")]
+RSVD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("rsvd_")]
 
 
 def _split(A, P):
@@ -111,3 +113,26 @@ def test_oracle_vs_reference_c_averaging():
     lib.dsubtract_mean(_p(Y), _p(X), _p(mean), ctypes.c_int(777), ctypes.c_int(37))
     assert np.abs(mean - po.temporal_mean(X)).max() <= 4e-16 * np.abs(X).max() * 37
     assert np.abs(Y - po.subtract_mean(X, mean)).max() == 0.0
+
+
+@pytest.mark.parametrize("path", RSVD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_randomized_svd_against_reference_golden(path):
+    """randomized_qr / randomized_svd / POD.run(randomized=True) of the oracle against the reference's own Python
+    (one rank), and the P = 2, 3 simulated-rank runs against the same fixture (the sketch is the same on all ranks)."""
+    g = np.load(path)
+    A, r, q, sk = g["A"], int(g["r"]), int(g["q"]), int(g["seed"])
+    assert np.array_equal(po.sketch_matrix(A.shape[1], r, sk), g["omega"])
+    assert len(RSVD_GOLDEN) >= 3
+    for P in (1, 2, 3):
+        blocks = [A[slice(*po.worksplit(0, A.shape[0], k, P))] for k in range(P)]
+        Q, B = po.randomized_qr(blocks, r, q, sk)
+        Q = np.vstack(Q)
+        assert np.abs(Q.T @ Q - np.eye(r)).max() <= 1e-13
+        assert np.abs(Q.T @ A - B).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+        assert np.abs(g["Q"] @ (g["Q"].T @ Q) - Q).max() <= 1e-9          # same range as the reference's Q
+        U, S, V = po.randomized_svd(blocks, r, q, sk)
+        mt = po.compare_svd(g["U"], g["S"], g["V"], np.vstack(U), S, V)
+        assert mt["sigma_rel"] <= 1e-12 and mt["mode_min"] >= 1 - 1e-8 and mt["vmode_min"] >= 1 - 1e-8, mt
+    U, S, V = po.pod_run(A, remove_mean=True, randomized=True, r=r, q=q, seed=sk)
+    mt = po.compare_svd(g["pod_U"], g["pod_S"], g["pod_V"], U, S, V)
+    assert mt["sigma_rel"] <= 1e-12 and mt["mode_min"] >= 1 - 1e-8, mt

@@ -49,6 +49,31 @@ for (m, n, remove_mean) in ((5000, 24, False), (40000, 151, True), (3001, 64, Tr
     if rank == 0:
         print(f"P={size} {m}x{n} mean={remove_mean}: sigma_rel={sig:.2e} mode_min={ipn[sel].min():.12f} vmode_min={vip[sel].min():.12f} "
               f"orth={orth:.2e} S_identical={same} rmse={rm:.3e}/{rmo:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+# ---- randomized path: matmulp (transposed-tall GEMM + all-reduce), tsqr of the sketch, rectangular svd
+for (m, n, r, q) in ((20000, 96, 12, 2), (size * 300, 40, 8, 1)):
+    X = synth.snapshots(m, n, 2022)
+    shards = [X[slice(*po.worksplit(0, m, k, size))] for k in range(size)]
+    r0, r1 = pl.utils.worksplit(0, m, rank, size)
+    Xd = torch.from_numpy(X[r0:r1].copy()).to(dev)
+    U, S, V = pl.POD.run(Xd, remove_mean=True, randomized=True, r=r, q=q, seed=11)
+    Uo, So, Vo = po.pod_run(shards, remove_mean=True, randomized=True, r=r, q=q, seed=11)
+    Sh, Vh = S.cpu().numpy(), V.cpu().numpy()
+    sig = np.abs(Sh - So).max() / So[0]
+    ip = torch.from_numpy(np.einsum("ik,ik->k", Uo[rank], U.cpu().numpy())).to(dev)
+    dist.all_reduce(ip)
+    ipn = np.abs(ip.cpu().numpy())
+    vip = np.abs(np.einsum("ki,ki->k", Vo, Vh))
+    G = U.T @ U
+    dist.all_reduce(G)
+    orth = float((G - torch.eye(r, dtype=torch.float64, device=dev)).abs().max())
+    Sall = [torch.zeros_like(S) for _ in range(size)]
+    dist.all_gather(Sall, S)
+    same = all(torch.equal(Sall[0], s) for s in Sall)
+    good = sig <= 1e-10 and ipn.min() >= 1 - 1e-8 and vip.min() >= 1 - 1e-8 and orth <= 1e-12 and same
+    ok &= bool(good)
+    if rank == 0:
+        print(f"P={size} randomized {m}x{n} r={r} q={q}: sigma_rel={sig:.2e} mode_min={ipn.min():.12f} vmode_min={vip.min():.12f} "
+              f"orth={orth:.2e} S_identical={same} -> {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)

@@ -119,6 +119,17 @@ class CudaEngine:
     def allgather_rows(self, R):
         return parall.mpi_allgather_rows(R)
 
+    def matmul(self, A, B):
+        from .maths import matmul
+        return matmul(A, B)
+
+    def matmul_tn(self, X, Y):
+        from .maths import matmul_tn
+        return matmul_tn(X, Y)
+
+    def svd_any(self, A):
+        return _svd_dev(A)
+
 
 _engine = CudaEngine()
 
@@ -159,22 +170,26 @@ def tsqr_svd(Ai):
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)
 
 
-@cr('math.tsqr')
-def tsqr(Ai):
-    """Parallel QR: Qi(m_i,n), R(n,n) identical on all ranks (pyLOM/vmmath/svd.py:49-118)."""
-    Ad, kind = _dev.to_device(Ai, "Ai")
+def _tsqr_dev(Ad, engine=None):
+    """Q_i (m_i, n), R (n, n) on device tensors: local Householder QR, one all-gather of the R_i, redundant QR of the stack."""
+    eng = engine or _engine
     _check_shape(Ad)
-    eng = _engine
     P, rank = parall.size(), parall.rank()
     m, n = Ad.shape
     R_i, _ = eng.factor(Ad, "local")
     if P == 1:
-        Q = eng.apply_q((m, n), None, "local", Ad.device)
-        return _dev.from_device(Q, kind), _dev.from_device(R_i, kind)
+        return eng.apply_q((m, n), None, "local", Ad.device), R_i
     Rstack = eng.allgather_rows(R_i)
     R, _ = eng.factor(Rstack, "stack")
     Q2 = eng.apply_q((P * n, n), None, "stack", Ad.device)
-    Q = eng.apply_q((m, n), Q2[rank * n:(rank + 1) * n], "local", Ad.device)
+    return eng.apply_q((m, n), Q2[rank * n:(rank + 1) * n], "local", Ad.device), R
+
+
+@cr('math.tsqr')
+def tsqr(Ai):
+    """Parallel QR: Qi(m_i,n), R(n,n) identical on all ranks (pyLOM/vmmath/svd.py:49-118)."""
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    Q, R = _tsqr_dev(Ad)
     return _dev.from_device(Q, kind), _dev.from_device(R, kind)
 
 
@@ -221,8 +236,10 @@ def _sketch_matrix(n, r, seed, device):
     return torch.from_numpy(np.random.RandomState(int(seed)).rand(int(n), int(r))).to(device)
 
 
-def _randomized_qr_dev(Ad, r, q, seed):
-    from .maths import matmul, matmulp
+def _randomized_qr_dev(Ad, r, q, seed, engine=None):
+    """randomized_qr on device tensors.  `matmulp(Ai.T, Qi)` / `matmulp(Qi.T, Ai)` of the reference are the
+    transposed-tall products X^T Y over the local rows followed by one all-reduce."""
+    eng = engine or _engine
     m, n = Ad.shape
     r = int(r)
     if not 1 <= r <= n:
@@ -231,14 +248,21 @@ def _randomized_qr_dev(Ad, r, q, seed):
         raise ValueError(f"every rank needs at least r rows (got m_i={m} < r={r})")
     seed = int(time.time()) if seed < 0 else int(seed)
     omega = _sketch_matrix(n, r, seed, Ad.device)
-    Yi = matmul(Ad, omega)
+    Yi = eng.matmul(Ad, omega)
     for _ in range(int(q)):                    # power iterations, re-orthonormalised each time
-        Qi, _R = tsqr(Yi)
-        Q2i = matmulp(Ad.T, Qi)
-        Yi = matmul(Ad, Q2i)
-    Qi, _R = tsqr(Yi)
-    B = matmulp(Qi.T, Ad)
+        Qi, _R = _tsqr_dev(Yi, eng)
+        Q2i = parall.mpi_reduce(eng.matmul_tn(Ad, Qi), op='sum', all=True)      # (n, r) = A^T Q
+        Yi = eng.matmul(Ad, Q2i)
+    Qi, _R = _tsqr_dev(Yi, eng)
+    B = parall.mpi_reduce(eng.matmul_tn(Qi, Ad), op='sum', all=True)            # (r, n) = Q^T A
     return Qi, B
+
+
+def _randomized_svd_dev(Ad, r, q, seed, engine=None):
+    eng = engine or _engine
+    Qi, B = _randomized_qr_dev(Ad, r, q, seed, eng)
+    Ur, S, V = eng.svd_any(B)
+    return eng.matmul(Qi, Ur), S, V
 
 
 @cr('math.randomized_qr')
@@ -254,9 +278,6 @@ def randomized_qr(Ai, r, q, seed=-1):
 def randomized_svd(Ai, r, q, seed=-1):
     """Randomized SVD (pyLOM/vmmath/svd.py:254-273; drandomized_svd src/svd.c:1453-1519):
     Ai (m_i, n) -> Ui (m_i, r), S (r), V (r, n) = V^T."""
-    from .maths import matmul
     Ad, kind = _dev.to_device(Ai, "Ai")
-    Qi, B = _randomized_qr_dev(Ad, r, q, seed)
-    Ur, S, V = _svd_dev(B)
-    Ui = matmul(Qi, Ur)
+    Ui, S, V = _randomized_svd_dev(Ad, r, q, seed)
     return _dev.from_device(Ui, kind), _dev.from_device(S, kind), _dev.from_device(V, kind)

@@ -96,6 +96,10 @@ GLOO_SCRIPT = textwrap.dedent("""
             U, S, V = np.linalg.svd(R.numpy()); return torch.from_numpy(U), torch.from_numpy(S), torch.from_numpy(V)
         def tsqr_svd_single(self, A, center=False): raise AssertionError('single-rank path in a 2-rank run')
         def allgather_rows(self, R): return parall.mpi_allgather_rows(R)
+        def matmul(self, A, B): return torch.from_numpy(A.numpy() @ B.numpy())
+        def matmul_tn(self, X, Y): return torch.from_numpy(X.numpy().T @ Y.numpy())
+        def svd_any(self, A):
+            U, S, V = np.linalg.svd(A.numpy(), full_matrices=False); return torch.from_numpy(U), torch.from_numpy(S), torch.from_numpy(V)
 
     rank, size = parall.init_distributed('gloo')
     assert size == 2 and parall.MPI_SIZE == 2
@@ -115,6 +119,14 @@ GLOO_SCRIPT = textwrap.dedent("""
     Sg = [torch.zeros_like(S) for _ in range(2)]; dist.all_gather(Sg, S)
     assert torch.equal(Sg[0], Sg[1])            # identical on all ranks
     assert abs(float(parall.mpi_reduce(1.0)) - 2.0) < 1e-15
+    # randomized path: sketch, power iterations (tsqr + matmulp = local X^T Y + all-reduce), rectangular svd
+    Y = A - A.mean(1, keepdims=True)
+    Ur_, Sr_, Vr_ = plsvd._randomized_svd_dev(torch.from_numpy(Y[r0:r1].copy()), 5, 2, 9, engine=CpuEngine())
+    Ul, So, Vo = po.pod_run([A[slice(*po.worksplit(0, m, r, 2))] for r in range(2)], remove_mean=True, randomized=True, r=5, q=2, seed=9)
+    assert Ur_.shape == (r1 - r0, 5) and Vr_.shape == (5, n)
+    assert np.abs(Sr_.numpy() - So).max() < 1e-12 * So[0]
+    ip = parall.mpi_reduce(np.einsum('ik,ik->k', Ul[rank], Ur_.numpy()), op='sum')
+    assert np.abs(np.abs(ip) - 1).max() < 1e-8, ip
     dist.barrier(); dist.destroy_process_group()
     print('RANK_OK_%d' % rank, flush=True)
 """)

@@ -145,8 +145,13 @@ def main_rsvd(outdir):
         Up, Sp, Vp = ref.POD.run(A, remove_mean=True, randomized=True, r=r, q=q, seed=sk)
         np.random.seed(sk)
         omega = np.random.rand(n, r)
+        # streaming variant: first half of the snapshots, then the second half (svd.py:176-226)
+        n1 = n // 2
+        Qs1, Bs1, Ys1 = ref.svd.init_qr_streaming(np.ascontiguousarray(A[:, :n1]), r, q, seed=sk)
+        Qs2, Bs2, Ys2 = ref.svd.update_qr_streaming(np.ascontiguousarray(A[:, n1:]), Qs1, Bs1, Ys1.copy(), r, q)
         blob = {"A": A, "r": np.array(r), "q": np.array(q), "seed": np.array(sk), "omega": omega,
-                "Q": Q, "B": B, "U": U, "S": S, "V": V, "pod_U": Up, "pod_S": Sp, "pod_V": Vp}
+                "Q": Q, "B": B, "U": U, "S": S, "V": V, "pod_U": Up, "pod_S": Sp, "pod_V": Vp,
+                "st_n1": np.array(n1), "st_Q1": Qs1, "st_B1": Bs1, "st_Y1": Ys1, "st_Q2": Qs2, "st_B2": Bs2, "st_Y2": Ys2}
         path = os.path.join(outdir, name + ".npz")
         np.savez_compressed(path, **blob)
         print(name, S[:3], os.path.getsize(path) // 1024, "KiB")

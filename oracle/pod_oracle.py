@@ -221,6 +221,49 @@ def randomized_qr(A_list, r: int, q: int, seed: int):
     return (Q[0] if single else Q), B
 
 
+_stream_rng = None      # the reference keeps drawing from numpy's global generator between the streaming calls
+
+
+def init_qr_streaming(A_list, r: int, q: int, seed: int):
+    """First block of the streaming randomized QR (pyLOM/vmmath/svd.py:176-200): randomized_qr that also returns the
+    sketch Y_i.  Seeds the generator the following update_qr_streaming calls keep drawing from."""
+    global _stream_rng
+    single = isinstance(A_list, np.ndarray)
+    As = [A_list] if single else A_list
+    n = As[0].shape[1]
+    _stream_rng = np.random.RandomState(seed)
+    omega = _stream_rng.rand(n, r)
+    Y = [matmul(A, omega) for A in As]
+    for _ in range(q):
+        Q, _R = tsqr(Y)
+        Q2 = matmulp([A.T for A in As], Q)
+        Y = [matmul(A, Q2) for A in As]
+    Q, _R = tsqr(Y)
+    B = matmulp([Qi.T for Qi in Q], As)
+    return (Q[0], B, Y[0]) if single else (Q, B, Y)
+
+
+def update_qr_streaming(A_list, Q1, B1, Yo, r: int, q: int):
+    """Next block of snapshots (same rows, new columns) (pyLOM/vmmath/svd.py:202-226): a fresh sketch of the new
+    block is power-iterated, added to the running Y, re-orthonormalised; B is carried over through Q2^T Q1."""
+    single = isinstance(A_list, np.ndarray)
+    As = [A_list] if single else A_list
+    Q1s = [Q1] if single else Q1
+    Yos = [Yo] if single else Yo
+    n = As[0].shape[1]
+    omega = _stream_rng.rand(n, r)
+    Yn = [matmul(A, omega) for A in As]
+    for _ in range(q):
+        Qp, _R = tsqr(Yn)
+        O2 = matmulp([A.T for A in As], Qp)
+        Yn = [matmul(A, O2) for A in As]
+    Yos = [a + b for a, b in zip(Yos, Yn)]
+    Q2, _R = tsqr(Yos)
+    Q2Q1 = matmulp([x.T for x in Q2], Q1s)
+    B2 = np.hstack((matmul(Q2Q1, B1), matmulp([x.T for x in Q2], As)))
+    return (Q2[0], B2, Yos[0]) if single else (Q2, B2, Yos)
+
+
 def randomized_svd(A_list, r: int, q: int, seed: int):
     """Randomized SVD (pyLOM/vmmath/svd.py:254-273; drandomized_svd, src/svd.c:1453-1519):
     ([U_i (m_i, r)], S (r), V (r, n))."""

@@ -4,4 +4,5 @@ from .maths import matmul, matmulp, vecmat, vector_sum, vector_norm
 from .averaging import temporal_mean, subtract_mean, temporal_variance, norm_variance
 from .truncation import compute_truncation_residual
 from .stats import RMSE
-from .svd import qr, svd, tsqr, tsqr_svd, randomized_qr, randomized_svd, next_power_of_2
+from .svd import (qr, svd, tsqr, tsqr_svd, randomized_qr, randomized_svd, init_qr_streaming, update_qr_streaming,
+                  next_power_of_2)

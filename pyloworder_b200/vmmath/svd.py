@@ -14,6 +14,7 @@ all-gather tree gives the same R up to row signs.  S and VT are identical on all
 import os
 import time
 
+import numpy as _np
 import torch
 
 from .. import _lib, _dev
@@ -228,39 +229,50 @@ def svd(A, method='gesdd'):
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)
 
 
-def _sketch_matrix(n, r, seed, device):
-    """omega = rand(n, r) from numpy's MT19937 seeded with `seed`: the same numbers the reference draws with
+def _sketch_matrix(n, r, rng, device):
+    """omega = rand(n, r) from numpy's MT19937: the same numbers the reference draws with
     `np.random.seed(seed); np.random.rand(n, r)` (pyLOM/vmmath/svd.py:131-133), generated on the host (n*r values)
-    without touching numpy's global generator."""
-    import numpy as np
-    return torch.from_numpy(np.random.RandomState(int(seed)).rand(int(n), int(r))).to(device)
+    from a private RandomState, i.e. without touching numpy's global generator."""
+    return torch.from_numpy(rng.rand(int(n), int(r))).to(device)
 
 
-def _randomized_qr_dev(Ad, r, q, seed, engine=None):
-    """randomized_qr on device tensors.  `matmulp(Ai.T, Qi)` / `matmulp(Qi.T, Ai)` of the reference are the
-    transposed-tall products X^T Y over the local rows followed by one all-reduce."""
-    eng = engine or _engine
-    m, n = Ad.shape
+def _power_sketch(Ad, omega, q, eng):
+    """Y = A (A^T A)^q omega with a TSQR re-orthonormalisation between the products (the loop at svd.py:134-140).
+    `matmulp(Ai.T, Qi)` of the reference = the transposed-tall product X^T Y over the local rows + one all-reduce."""
+    Yi = eng.matmul(Ad, omega)
+    for _ in range(int(q)):
+        Qi, _R = _tsqr_dev(Yi, eng)
+        Q2i = parall.mpi_reduce(eng.matmul_tn(Ad, Qi), op='sum', all=True)      # (n, r) = A^T Q
+        Yi = eng.matmul(Ad, Q2i)
+    return Yi
+
+
+def _check_sketch_shape(m, n, r):
     r = int(r)
     if not 1 <= r <= n:
         raise ValueError(f"randomized_qr: need 1 <= r <= n (got r={r}, n={n})")
     if m < r:
         raise ValueError(f"every rank needs at least r rows (got m_i={m} < r={r})")
-    seed = int(time.time()) if seed < 0 else int(seed)
-    omega = _sketch_matrix(n, r, seed, Ad.device)
-    Yi = eng.matmul(Ad, omega)
-    for _ in range(int(q)):                    # power iterations, re-orthonormalised each time
-        Qi, _R = _tsqr_dev(Yi, eng)
-        Q2i = parall.mpi_reduce(eng.matmul_tn(Ad, Qi), op='sum', all=True)      # (n, r) = A^T Q
-        Yi = eng.matmul(Ad, Q2i)
+    return r
+
+
+def _randomized_qr_dev(Ad, r, q, seed, engine=None, rng=None):
+    """randomized_qr on device tensors: returns Q_i (m_i, r), B (r, n) = Q^T A and the sketch Y_i."""
+    eng = engine or _engine
+    m, n = Ad.shape
+    r = _check_sketch_shape(m, n, r)
+    if rng is None:
+        rng = _np.random.RandomState(int(time.time()) if seed is None or seed < 0 else int(seed))
+    omega = _sketch_matrix(n, r, rng, Ad.device)
+    Yi = _power_sketch(Ad, omega, q, eng)
     Qi, _R = _tsqr_dev(Yi, eng)
     B = parall.mpi_reduce(eng.matmul_tn(Qi, Ad), op='sum', all=True)            # (r, n) = Q^T A
-    return Qi, B
+    return Qi, B, Yi
 
 
 def _randomized_svd_dev(Ad, r, q, seed, engine=None):
     eng = engine or _engine
-    Qi, B = _randomized_qr_dev(Ad, r, q, seed, eng)
+    Qi, B, _Y = _randomized_qr_dev(Ad, r, q, seed, eng)
     Ur, S, V = eng.svd_any(B)
     return eng.matmul(Qi, Ur), S, V
 
@@ -270,8 +282,45 @@ def randomized_qr(Ai, r, q, seed=-1):
     """Randomized range finder (pyLOM/vmmath/svd.py:120-144; drandomized_qr src/svd.c:1267-1319):
     Ai (m_i, n) -> Qi (m_i, r) orthonormal over all ranks, B (r, n) = Q^T A identical on all ranks."""
     Ad, kind = _dev.to_device(Ai, "Ai")
-    Qi, B = _randomized_qr_dev(Ad, r, q, seed)
+    Qi, B, _Y = _randomized_qr_dev(Ad, r, q, seed)
     return _dev.from_device(Qi, kind), _dev.from_device(B, kind)
+
+
+_stream_rng = None      # the reference keeps drawing from numpy's global generator between the streaming calls
+
+
+@cr('math.init_qr_streaming')
+def init_qr_streaming(Ai, r, q, seed=None):
+    """First block of the streaming randomized QR (pyLOM/vmmath/svd.py:176-200): randomized_qr that also returns
+    the sketch Yi (m_i, r).  Seeds the generator the following update_qr_streaming calls draw from."""
+    global _stream_rng
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    _stream_rng = _np.random.RandomState(int(time.time()) if seed is None else int(seed))
+    Qi, B, Yi = _randomized_qr_dev(Ad, r, q, None, rng=_stream_rng)
+    return _dev.from_device(Qi, kind), _dev.from_device(B, kind), _dev.from_device(Yi, kind)
+
+
+@cr('math.qr_iteration')
+def update_qr_streaming(Ai, Q1, B1, Yo, r, q):
+    """Next block of snapshots -- same rows, new columns (pyLOM/vmmath/svd.py:202-226): Ai (m_i, n2), Q1 (m_i, r),
+    B1 (r, n1), Yo (m_i, r)  ->  Q2 (m_i, r), B2 (r, n1 + n2), Yo + Yn."""
+    global _stream_rng
+    eng = _engine
+    Ad, kind = _dev.to_device(Ai, "Ai")
+    Q1d, _ = _dev.to_device(Q1, "Q1")
+    B1d, _ = _dev.to_device(B1, "B1")
+    Yod, _ = _dev.to_device(Yo, "Yo")
+    m, n = Ad.shape
+    r = _check_sketch_shape(m, n, r)
+    if _stream_rng is None:
+        _stream_rng = _np.random.RandomState()
+    Yn = _power_sketch(Ad, _sketch_matrix(n, r, _stream_rng, Ad.device), q, eng)
+    Ynew = Yod + Yn
+    Q2, _R = _tsqr_dev(Ynew, eng)
+    Q2Q1 = parall.mpi_reduce(eng.matmul_tn(Q2, Q1d), op='sum', all=True)        # (r, r)
+    B2n = parall.mpi_reduce(eng.matmul_tn(Q2, Ad), op='sum', all=True)          # (r, n2)
+    B2 = torch.cat((eng.matmul(Q2Q1, B1d), B2n), dim=1)
+    return _dev.from_device(Q2, kind), _dev.from_device(B2, kind), _dev.from_device(Ynew, kind)
 
 
 @cr('math.randomized_svd')

@@ -327,6 +327,30 @@ def test_randomized_svd_against_reference_golden(pl, path):
     assert isinstance(Un, np.ndarray) and np.abs(Sn - S).max() <= 1e-12 * S[0]
 
 
+@pytest.mark.parametrize("path", RSVD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_streaming_randomized_qr(pl, path):
+    """init_qr_streaming / update_qr_streaming.  The first block is range-identical to the reference's; the update
+    adds two sketches whose column signs come from the QR (result depends on the QR's sign convention, also between
+    the reference's own P = 1 and P = 2 runs), so it is checked through the identities the algorithm guarantees and
+    through the approximation error, which must be as good as the reference's."""
+    g = np.load(path)
+    A, r, q, sk, n1 = g["A"], int(g["r"]), int(g["q"]), int(g["seed"]), int(g["st_n1"])
+    A1, A2 = np.ascontiguousarray(A[:, :n1]), np.ascontiguousarray(A[:, n1:])
+    Q1, B1, Y1 = pl.math.init_qr_streaming(dev(A1), r, q, seed=sk)
+    Q1h = host(Q1)
+    assert np.abs(g["st_Q1"] @ (g["st_Q1"].T @ Q1h) - Q1h).max() <= 1e-9          # same range as the reference's Q1
+    assert np.abs(Q1h.T @ A1 - host(B1)).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+    Q2, B2, Y2 = [host(t) for t in pl.math.update_qr_streaming(dev(A2), Q1, B1, Y1, r, q)]
+    assert Q2.shape == (A.shape[0], r) and B2.shape == (r, A.shape[1]) and Y2.shape == (A.shape[0], r)
+    assert np.abs(Q2.T @ Q2 - np.eye(r)).max() <= 1e-12
+    assert np.abs(Q2 @ (Q2.T @ Y2) - Y2).max() <= 1e-10 * np.abs(Y2).max()
+    assert np.abs(B2[:, n1:] - Q2.T @ A2).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+    assert np.abs(B2[:, :n1] - (Q2.T @ Q1h) @ host(B1)).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+    err = np.linalg.norm(A - Q2 @ B2) / np.linalg.norm(A)
+    err_ref = np.linalg.norm(A - g["st_Q2"] @ g["st_B2"]) / np.linalg.norm(A)
+    assert err <= 2.0 * err_ref + 1e-12, (err, err_ref)
+
+
 @pytest.mark.parametrize("m,n,r,q", [(200000, 128, 16, 2), (60000, 512, 40, 1), (30000, 151, 10, 3)])
 def test_randomized_svd_against_oracle(pl, m, n, r, q):
     A = synth.snapshots(m, n, 31)

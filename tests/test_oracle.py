@@ -136,3 +136,28 @@ def test_randomized_svd_against_reference_golden(path):
     U, S, V = po.pod_run(A, remove_mean=True, randomized=True, r=r, q=q, seed=sk)
     mt = po.compare_svd(g["pod_U"], g["pod_S"], g["pod_V"], U, S, V)
     assert mt["sigma_rel"] <= 1e-12 and mt["mode_min"] >= 1 - 1e-8, mt
+
+
+@pytest.mark.parametrize("path", RSVD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_streaming_randomized_qr_against_reference_golden(path):
+    """init_qr_streaming / update_qr_streaming: one rank reproduces the reference bit for bit (same LAPACK, same
+    MT19937 stream).  The update ADDS two sketches whose column signs come from the QR, so its result depends on the
+    QR's sign convention (the reference's own P = 2 run differs from its P = 1 run); for P = 2 only the identities
+    the algorithm guarantees are checked."""
+    g = np.load(path)
+    A, r, q, sk, n1 = g["A"], int(g["r"]), int(g["q"]), int(g["seed"]), int(g["st_n1"])
+    A1, A2 = np.ascontiguousarray(A[:, :n1]), np.ascontiguousarray(A[:, n1:])
+    Q1, B1, Y1 = po.init_qr_streaming(A1, r, q, sk)
+    assert np.array_equal(Q1, g["st_Q1"]) and np.array_equal(B1, g["st_B1"]) and np.array_equal(Y1, g["st_Y1"])
+    Q2, B2, Y2 = po.update_qr_streaming(A2, Q1, B1, Y1, r, q)
+    assert np.array_equal(Q2, g["st_Q2"]) and np.array_equal(B2, g["st_B2"]) and np.array_equal(Y2, g["st_Y2"])
+    P = 2
+    cut = lambda X: [X[slice(*po.worksplit(0, X.shape[0], k, P))] for k in range(P)]
+    Q1, B1, Y1 = po.init_qr_streaming(cut(A1), r, q, sk)
+    Q2, B2, Y2 = po.update_qr_streaming(cut(A2), Q1, B1, Y1, r, q)
+    Q1, Q2, Y2 = np.vstack(Q1), np.vstack(Q2), np.vstack(Y2)
+    assert B2.shape == (r, A.shape[1])
+    assert np.abs(Q2.T @ Q2 - np.eye(r)).max() <= 1e-13
+    assert np.abs(Q2 @ (Q2.T @ Y2) - Y2).max() <= 1e-10 * np.abs(Y2).max()
+    assert np.abs(B2[:, n1:] - Q2.T @ A2).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+    assert np.abs(B2[:, :n1] - (Q2.T @ Q1) @ B1).max() <= 1e-12 * np.abs(A).max() * A.shape[1]

@@ -78,6 +78,12 @@ def _load_rank(world, rank):
                 setattr(vm, k, v)
         setattr(out, name, m)
     out.POD = load("POD.wrapper", "POD/wrapper.py")
+    for k, v in vars(out.POD).items():
+        if callable(v) and not k.startswith("_"):
+            setattr(pod, k, v)
+    utils.cr_start, utils.cr_stop = cr.cr_start, cr.cr_stop
+    mod(tag + ".DMD", True)
+    out.DMD = load("DMD.wrapper", "DMD/wrapper.py")
     return out
 
 
@@ -157,12 +163,44 @@ def main_rsvd(outdir):
         print(name, S[:3], os.path.getsize(path) // 1024, "KiB")
 
 
+# DMD on the POD basis (pyLOM/DMD/wrapper.py:50-146): travelling / decaying waves + noise, so that the eigenvalues are
+# well separated conjugate pairs.
+DMD_CASES = [
+    # name, m, n, seed, r, ranks
+    ("dmd_waves_600x48", 600, 48, 3, 8, (1, 2)),
+    ("dmd_waves_1500x80_res", 1500, 80, 4, 1e-4, (1, 3)),
+]
+
+
+def main_dmd(outdir):
+    for name, m, n, seed, r, ranks in DMD_CASES:
+        X = synth.dmd_waves(m, n, seed)
+        blob = {"X": X, "r": np.array(r), "dt": np.array(0.1)}
+        for P in ranks:
+            res = run_ranks(lambda ref, Xi: ref.DMD.run(Xi, r, remove_mean=True), split_rows(X, P))
+            muR, muI, _, b = res[0]
+            Phi = np.vstack([x[2] for x in res])
+            blob[f"P{P}_muReal"], blob[f"P{P}_muImag"], blob[f"P{P}_Phi"], blob[f"P{P}_b"] = muR, muI, Phi, b
+            if P == 1:
+                ref = _load_rank(_World(1), 0)
+                delta, omega = ref.DMD.frequency_damping(muR, muI, 0.1)
+                t = np.arange(n, dtype=np.double)
+                blob["delta"], blob["omega"] = delta, omega
+                blob["X_DMD"] = ref.DMD.reconstruction_jovanovic(Phi, muR, muI, t, b)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, blob["P1_muReal"][:4], blob["P1_muImag"][:4], os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     outdir = os.path.join(HERE, "..", "tests", "golden")
+    if "--dmd" in sys.argv:
+        return main_dmd(outdir)
     os.makedirs(outdir, exist_ok=True)
     if "--rsvd" in sys.argv:           # only the randomized fixtures (leaves the others untouched)
         return main_rsvd(outdir)
     main_rsvd(outdir)
+    main_dmd(outdir)
     for name, m, n, kind, seed, ranks in CASES:
         A = make_input(m, n, kind, seed)
         blob = {"A": A}

@@ -294,6 +294,101 @@ def pod_run(X_list, remove_mean: bool = True, divide_variance: bool = False, ran
     return (U[0] if single else U), S, V
 
 
+# --------------------------------------------------------------------------------------
+# DMD on the POD basis
+# --------------------------------------------------------------------------------------
+def vandermonde(real, imag, m, n):
+    """Vand[:, k] = (real + i imag)**k, k < n  (pyLOM/vmmath/maths.py:202-222)."""
+    Vand = np.zeros((m, n), dtype=np.complex128)
+    for icol in range(n):
+        Vand[:, icol] = (real + imag * 1j) ** icol
+    return Vand
+
+
+def vandermonde_time(real, imag, m, time):
+    """Vand[:, it] = (real + i imag)**t  (pyLOM/vmmath/maths.py:224-246)."""
+    Vand = np.zeros((m, time.shape[0]), dtype=np.complex128)
+    for it, t in enumerate(time):
+        Vand[:, it] = (real + imag * 1j) ** t
+    return Vand
+
+
+def dmd_order_modes(muReal, muImag, Phi, bJov):
+    """Sort by decreasing |b| and put the positive-imaginary member of every conjugate pair first
+    (pyLOM/DMD/wrapper.py:18-47, statement for statement -- including what it does to Phi.imag and bJov.imag)."""
+    order = np.flip(np.abs(bJov).argsort())
+    muReal = muReal[order]
+    muImag = muImag[order]
+    Phi = np.transpose(np.transpose(Phi)[order])
+    bJov = bJov[order]
+    p = False
+    for ii in range(muImag.shape[0]):
+        if p:
+            p = False
+            continue
+        iimag = muImag[ii]
+        if iimag < 0:
+            muImag[ii] = muImag[ii + 1]
+            muImag[ii + 1] = -muImag[ii]
+            bJov.imag[ii] = bJov.imag[ii + 1]
+            bJov.imag[ii + 1] = -bJov.imag[ii]
+            Phi.imag[:, ii] = Phi.imag[:, ii + 1]
+            Phi.imag[:, ii + 1] = -Phi.imag[:, ii + 1]
+            p = True
+            continue
+        if iimag > 0:
+            p = True
+            continue
+    return muReal, muImag, Phi, bJov
+
+
+def dmd_run(X_list, r, remove_mean: bool = True):
+    """DMD.run on P simulated ranks (pyLOM/DMD/wrapper.py:50-117): SVD of the first n-1 snapshots, projected linear
+    map Atilde = U^T Y2 V S^-1, its eigen-decomposition, modes Phi = Y2 V S^-1 w / mu, Jovanovic amplitudes."""
+    single = isinstance(X_list, np.ndarray)
+    Xs = [X_list] if single else X_list
+    Ys = [subtract_mean(X, temporal_mean(X)) for X in Xs] if remove_mean else [X.copy() for X in Xs]
+    U, S, VT = tsqr_svd([np.ascontiguousarray(Y[:, :-1]) for Y in Ys])
+    N = int(r) if r >= 1 else compute_truncation_residual(S, r)
+    U = [Ui[:, :N] for Ui in U]; S = S[:N]; VT = VT[:N, :]
+    aux1 = matmulp([Ui.T for Ui in U], [Y[:, 1:] for Y in Ys])
+    aux2 = np.transpose(vecmat(1. / S, VT))
+    Atilde = matmul(aux1, aux2)
+    mu, w = np.linalg.eig(Atilde)
+    muReal, muImag = np.real(mu), np.imag(mu)
+    Phi = [matmul(matmul(matmul(Y[:, 1:], np.transpose(VT)), np.diag(1 / S)), w) / (muReal + muImag * 1J) for Y in Ys]
+    Vand = vandermonde(muReal, muImag, muReal.shape[0], Ys[0].shape[1] - 1)
+    P = matmul(np.transpose(np.conj(w)), w) * np.conj(matmul(Vand, np.transpose(np.conj(Vand))))
+    Pl = np.linalg.cholesky(P)
+    G = matmul(np.diag(S), VT)
+    q = np.conj(np.diag(matmul(matmul(Vand, np.transpose(np.conj(G))), w)))
+    bJov = matmul(np.linalg.inv(np.transpose(np.conj(Pl))), matmul(np.linalg.inv(Pl), q))
+    Phi_all = np.vstack(Phi)
+    muReal, muImag, Phi_all, bJov = dmd_order_modes(muReal, muImag, Phi_all, bJov)
+    if single:
+        return muReal, muImag, Phi_all, bJov
+    cuts = np.cumsum([0] + [Y.shape[0] for Y in Ys])
+    return muReal, muImag, [Phi_all[cuts[k]:cuts[k + 1]] for k in range(len(Ys))], bJov
+
+
+def dmd_frequency_damping(real, imag, dt):
+    """pyLOM/DMD/wrapper.py:119-130."""
+    mod = np.sqrt(real * real + imag * imag)
+    arg = np.arctan2(imag, real)
+    return np.log(mod) / dt, arg / dt
+
+
+def dmd_mode_computation(X, V, S, W):
+    """pyLOM/DMD/wrapper.py:132-138."""
+    return matmul(matmul(matmul(X, np.transpose(V)), np.diag(1 / S)), np.abs(W))
+
+
+def dmd_reconstruction_jovanovic(Phi, real, imag, t, bJov):
+    """pyLOM/DMD/wrapper.py:140-146."""
+    Vand = vandermonde_time(real, imag, real.shape[0], t)
+    return matmul(Phi, matmul(np.diag(bJov), Vand)).real
+
+
 def vector_norm(v, start=0):
     """pyLOM/vmmath/maths.py:47-59."""
     return np.linalg.norm(v[start:], 2)

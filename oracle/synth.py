@@ -57,3 +57,21 @@ def random_matrix(m, n, seed, cond=None):
         Uq, _ = np.linalg.qr(A)
         A = (Uq * s) @ Vq.T
     return np.ascontiguousarray(A)
+
+
+def dmd_waves(m, n, seed, npairs=4, dt=0.1, noise=1e-6):
+    """Snapshots of a linear system with `npairs` damped / growing travelling waves (distinct frequencies and decay
+    rates, so the DMD eigenvalues are well separated conjugate pairs) + a steady offset + hashed noise."""
+    i = np.arange(m, dtype=np.int64)
+    j = np.arange(n, dtype=np.int64)
+    x = (i + 0.5) / m
+    t = j * dt
+    X = np.repeat((1.0 + 0.3 * np.sin(2 * np.pi * x))[:, None], n, axis=1)
+    for k in range(npairs):
+        amp = 2.0 ** (-k)
+        om = 2.0 + 1.7 * k
+        sig = -0.05 * (k + 1) + (0.04 if k == 1 else 0.0)
+        phase = 2 * np.pi * (k + 1) * x + 0.5 * k
+        X += amp * np.exp(sig * t)[None, :] * np.cos(phase[:, None] - om * t[None, :])
+    X += noise * _hash01(seed, i, j)
+    return np.ascontiguousarray(X)

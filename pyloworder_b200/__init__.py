@@ -7,6 +7,6 @@ NVIDIA B200 (sm_100a): hand-written CUDA behind a C ABI, same Python names and s
 """
 __version__ = "0.1.0"
 
-from . import utils, vmmath, POD
+from . import utils, vmmath, POD, DMD
 from . import vmmath as math
 from .utils import pprint, cr_info, gpu_device, gpu_to_cpu, cpu_to_gpu

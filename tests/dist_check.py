@@ -74,6 +74,21 @@ for (m, n, r, q) in ((20000, 96, 12, 2), (size * 300, 40, 8, 1)):
     if rank == 0:
         print(f"P={size} randomized {m}x{n} r={r} q={q}: sigma_rel={sig:.2e} mode_min={ipn.min():.12f} vmode_min={vip.min():.12f} "
               f"orth={orth:.2e} S_identical={same} -> {'OK' if good else 'FAIL'}", flush=True)
+# ---- DMD on the POD basis: projection U^T Y2 through matmulp (all-reduce), modes as interleaved-complex GEMM
+for (m, n, r) in ((6000, 48, 8),):
+    X = synth.dmd_waves(m, n, 3)
+    shards = [X[slice(*po.worksplit(0, m, k, size))] for k in range(size)]
+    r0, r1 = pl.utils.worksplit(0, m, rank, size)
+    muR, muI, Phi, b = pl.DMD.run(torch.from_numpy(X[r0:r1].copy()).to(dev), r, remove_mean=True)
+    muRo, muIo, Phio, bo = po.dmd_run(shards, r)
+    dmu = max(np.abs(muR.cpu().numpy() - muRo).max(), np.abs(muI.cpu().numpy() - muIo).max())
+    pb, pbo = Phi.cpu().numpy() * b.cpu().numpy(), Phio[rank] * bo
+    dpb = torch.tensor([np.abs(pb - pbo).max() / np.abs(bo).max()], device=dev)
+    dist.all_reduce(dpb, op=dist.ReduceOp.MAX)
+    good = dmu <= 1e-10 and float(dpb) <= 1e-6
+    ok &= bool(good)
+    if rank == 0:
+        print(f"P={size} DMD {m}x{n} r={r}: mu_abs={dmu:.2e} mode_amp_rel={float(dpb):.2e} -> {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)

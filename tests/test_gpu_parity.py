@@ -12,7 +12,8 @@ import synth
 
 pytestmark = pytest.mark.gpu
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("rsvd_")]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("rsvd_", "dmd_"))]
+DMD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("dmd_")]
 RSVD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("rsvd_")]
 
 SIG_TOL = 1e-10
@@ -360,6 +361,39 @@ def test_randomized_svd_against_oracle(pl, m, n, r, q):
     # the leading modes approximate the deterministic ones
     S_full = np.linalg.svd(A, compute_uv=False)
     assert np.abs(got[1][:4] - S_full[:4]).max() <= 1e-6 * S_full[0]
+
+
+@pytest.mark.parametrize("path", DMD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_dmd_against_reference_golden(pl, path):
+    """DMD.run / frequency_damping / reconstruction_jovanovic against the reference's own Python output.  Modes are
+    unique up to a unit complex factor per mode (LAPACK fixes only the norm of an eigenvector), so eigenvalues, |b|,
+    the products Phi_k b_k and the reconstruction are compared; the amplitudes solve a Vandermonde-Gram system with
+    cond ~ 1e8, hence 1e-6 there and 1e-10 on the eigenvalues."""
+    g = np.load(path)
+    X, r, dt = g["X"], float(g["r"]), float(g["dt"])
+    Xd = dev(X)
+    muR, muI, Phi, b = pl.DMD.run(Xd, r, remove_mean=True)
+    assert torch.equal(Xd, dev(X)), "DMD.run must not modify X"
+    assert Phi.dtype == torch.complex128 and Phi.shape == (X.shape[0], g["P1_muReal"].shape[0])
+    muRh, muIh, Phih, bh = host(muR), host(muI), host(Phi), host(b)
+    assert np.abs(muRh - g["P1_muReal"]).max() <= 1e-10 and np.abs(muIh - g["P1_muImag"]).max() <= 1e-10
+    bref, Pref = g["P1_b"], g["P1_Phi"]
+    assert np.abs(np.abs(bh) - np.abs(bref)).max() <= 1e-6 * np.abs(bref).max()
+    assert np.abs(Phih * bh - Pref * bref).max() <= 1e-6 * np.abs(Pref * bref).max()
+    assert np.all(muIh[0::2] >= 0)
+    delta, omega = pl.DMD.frequency_damping(muR, muI, dt)
+    assert np.abs(host(delta) - g["delta"]).max() <= 1e-9 and np.abs(host(omega) - g["omega"]).max() <= 1e-9
+    t = np.arange(X.shape[1], dtype=np.double)
+    Xr = host(pl.DMD.reconstruction_jovanovic(Phi, muR, muI, t, b))
+    assert np.abs(Xr - g["X_DMD"]).max() <= 1e-6 * np.abs(g["X_DMD"]).max()
+    # numpy in -> numpy out
+    muRn, muIn, Phin, bn = pl.DMD.run(X, r, remove_mean=True)
+    assert isinstance(Phin, np.ndarray) and Phin.dtype == np.complex128 and np.abs(muRn - muRh).max() <= 1e-12
+    # mode_computation: X V^T S^-1 |W|
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((5, X.shape[1])); S = rng.random(5) + 0.5; W = rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))
+    Mc = host(pl.DMD.mode_computation(Xd, V, S, W))
+    assert np.abs(Mc - po.dmd_mode_computation(X, V, S, W)).max() <= 1e-11 * np.abs(Mc).max()
 
 
 def test_large_properties(pl):

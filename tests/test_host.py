@@ -54,7 +54,7 @@ def test_truncation_rule_matches_golden(golden_dir):
     from pyloworder_b200.vmmath import compute_truncation_residual
     import glob
     for path in glob.glob(os.path.join(golden_dir, "*.npz")):
-        if os.path.basename(path).startswith("rsvd_"):
+        if os.path.basename(path).startswith(("rsvd_", "dmd_")):
             continue
         g = np.load(path)
         S = g["tsqr_svd_P1_S"]

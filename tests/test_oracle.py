@@ -9,7 +9,8 @@ import pod_oracle as po
 import synth
 
 ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith("rsvd_")]
+GOLDEN = [p for p in ALL_GOLDEN if not os.path.basename(p).startswith(("rsvd_", "dmd_"))]
+DMD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("dmd_")]
 RSVD_GOLDEN = [p for p in ALL_GOLDEN if os.path.basename(p).startswith("rsvd_")]
 
 
@@ -161,3 +162,35 @@ def test_streaming_randomized_qr_against_reference_golden(path):
     assert np.abs(Q2 @ (Q2.T @ Y2) - Y2).max() <= 1e-10 * np.abs(Y2).max()
     assert np.abs(B2[:, n1:] - Q2.T @ A2).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
     assert np.abs(B2[:, :n1] - (Q2.T @ Q1) @ B1).max() <= 1e-12 * np.abs(A).max() * A.shape[1]
+
+
+def dmd_invariants(g, muR, muI, Phi, b, key="P1", mu_tol=1e-10, amp_tol=1e-6):
+    """DMD results are unique up to a unit complex factor c_k per mode (Phi_k -> c_k Phi_k, b_k -> b_k / c_k: LAPACK
+    only fixes the norm of an eigenvector) -- compare eigenvalues, |b|, the products Phi_k b_k and the reconstruction.
+    The amplitudes solve a Vandermonde-Gram system with cond ~ 1e8, hence the looser tolerance."""
+    assert np.abs(muR - g[key + "_muReal"]).max() <= mu_tol and np.abs(muI - g[key + "_muImag"]).max() <= mu_tol
+    bref, Pref = g[key + "_b"], g[key + "_Phi"]
+    assert np.abs(np.abs(b) - np.abs(bref)).max() <= amp_tol * np.abs(bref).max()
+    assert np.abs(Phi * b - Pref * bref).max() <= amp_tol * np.abs(Pref * bref).max()
+
+
+@pytest.mark.parametrize("path", DMD_GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_dmd_against_reference_golden(path):
+    g = np.load(path)
+    X, r, dt = g["X"], float(g["r"]), float(g["dt"])
+    assert len(DMD_GOLDEN) >= 2
+    muR, muI, Phi, b = po.dmd_run(X, r)
+    assert np.array_equal(muR, g["P1_muReal"]) and np.array_equal(Phi, g["P1_Phi"])      # same LAPACK, same statements
+    dmd_invariants(g, muR, muI, Phi, b)
+    assert np.all(muI[0::2] >= 0)                       # positive member of every conjugate pair first
+    delta, omega = po.dmd_frequency_damping(muR, muI, dt)
+    assert np.allclose(delta, g["delta"], rtol=0, atol=1e-12) and np.allclose(omega, g["omega"], rtol=0, atol=1e-12)
+    t = np.arange(X.shape[1], dtype=np.double)
+    Xd = po.dmd_reconstruction_jovanovic(Phi, muR, muI, t, b)
+    assert np.abs(Xd - g["X_DMD"]).max() <= 1e-6 * np.abs(g["X_DMD"]).max()
+    for key in [k[:-7] for k in g.files if k.endswith("_muReal") and k != "P1_muReal"]:
+        P = int(key[1:])
+        bl = [X[slice(*po.worksplit(0, X.shape[0], k, P))] for k in range(P)]
+        muR, muI, Phi, b = po.dmd_run(bl, r)
+        dmd_invariants(g, muR, muI, np.vstack(Phi), b, key)          # the reference's own P-rank run
+        dmd_invariants(g, muR, muI, np.vstack(Phi), b, "P1")

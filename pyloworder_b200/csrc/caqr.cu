@@ -414,8 +414,15 @@ struct UpdArgs {
   const double* Tl; const double* Vupl; const double* Vpivl; int virt;
   double* C0; int64_t ldc0; int coff0; int nchunk0;
   double* C1; int64_t ldc1; int coff1;
+  int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores
 };
 
+// Timing experiments (probes/upd_phase_probe.py): build with -DPL_UPD_EXPERIMENTS and set PL_UPD_DBG to skip phases.
+#ifdef PL_UPD_EXPERIMENTS
+#define UPD_DBG(bit) (A.dbg & (bit))
+#else
+#define UPD_DBG(bit) 0
+#endif
 __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSmem& S = *reinterpret_cast<UpdSmem*>(smem_raw);
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     const int64_t t = t0 + i;
     const bool first = (i == 0);
     // ---- stage V, C, T of this tile
-    {
+    if (!UPD_DBG(1) || it == 0) {
       const double* vp = vbase + t * v_tile;
       double* cp = cbase + t * c_tile;
 #pragma unroll
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     const double (*C0)[SP] = first ? S.Zs : S.Cs[0];   // slab 0 of the first tile is the carried block
 
     // ---- GEMM1: W = V^T C (+ Z)      four independent accumulator chains (one per slab)
-    {
+    if (!UPD_DBG(2)) {
       double acc[G][4];
 #pragma unroll
       for (int q = 0; q < G; q++) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     }
     __syncthreads();
     // ---- W' = op(T) W     forward: T^T, backward: T
-    {
+    if (!UPD_DBG(4)) {
       double acc[4] = {0, 0, 0, 0}, accb[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int kk = 0; kk < 2; kk++) {
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     }
     __syncthreads();
     // ---- GEMM2: C -= V W'     warp -> (slab gq, column half gh)
-    {
+    if (!UPD_DBG(8)) {
       const bool piv = first && gq == 0;
       double (*Cq)[SP] = piv ? S.Zs : S.Cs[gq];
       const bool valid = (t * G + gq) < A.nblk;
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
           if (piv) {
             *reinterpret_cast<double2*>(&S.Zs[r][c]) = make_double2(acc[0], acc[1]);
             *reinterpret_cast<double2*>(&S.Zs[r + 8][c]) = make_double2(acc[2], acc[3]);
-          } else if (valid) {
+          } else if (valid && !UPD_DBG(16)) {
             double* dst = crow + (int64_t)(16 * m2) * ldc + 8 * nn;
             *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
             *reinterpret_cast<double2*>(dst + 8 * ldc) = make_double2(acc[2], acc[3]);
@@ -649,6 +656,8 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   A.Vupl = (li > 0) ? (Vup + L.v_off * (TB * NB)) : nullptr;
   A.Vpivl = (li > 0) ? nullptr : (Vpiv + L.p_off * (NB * NB));
   A.virt = virt;
+  static const int upd_dbg = getenv("PL_UPD_DBG") ? atoi(getenv("PL_UPD_DBG")) : 0;
+  A.dbg = upd_dbg;
   A.C0 = C0; A.ldc0 = ldc0; A.coff0 = coff0; A.nchunk0 = nchunk0;
   A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1;
   static bool attr_set = false;

@@ -283,7 +283,7 @@ def run_ours(args):
     S_dev = S.cpu() if size == 1 else None
     del S, V
     # host memory: 2 pinned buffers of m_e2e x n per rank; with several ranks on one node the e2e sample is capped
-    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else 1_000_000)
+    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else 2_000_000)
     m_e2e = min(m, e2e_rows)
     try:
         host_in = torch.empty((m_e2e, n), dtype=torch.float64, pin_memory=True)
@@ -298,11 +298,21 @@ def run_ours(args):
                 rc = L.pl_tsqr_svd_host_f64(host_U.data_ptr(), host_S.data_ptr(), host_V.data_ptr(), host_in.data_ptr(), m_e2e, n)
                 _lib.check(rc, "pl_tsqr_svd_host_f64")
         else:
+            # P ranks from host memory: local chunked pipeline -> NCCL all-gather of the n x n R's -> SVD of the stack
+            # (redundant on every rank) -> local chunked back-multiply with this rank's block of Q2 Ur
+            Rl = torch.empty((n, n), dtype=torch.float64, device=dev)
+            Rst = torch.empty((size * n, n), dtype=torch.float64, device=dev)
+            Wst = torch.empty((size * n, n), dtype=torch.float64, device=dev)
+            Sd = torch.empty(n, dtype=torch.float64, device=dev); Vd = torch.empty((n, n), dtype=torch.float64, device=dev)
+            _, wp2, wb2 = _dev.workspace(L.pl_qr_workspace_bytes(size * n, n), "stack", dev)
             def e2e_step():
-                Ad = host_in.cuda(non_blocking=True)
-                Ue, Se, Ve = pl.math.tsqr_svd(Ad)
-                host_U.copy_(Ue, non_blocking=True); host_S.copy_(Se); host_V.copy_(Ve)
-                torch.cuda.synchronize()
+                _lib.check(L.pl_tsqr_host_factor_f64(Rl.data_ptr(), host_in.data_ptr(), m_e2e, n), "pl_tsqr_host_factor_f64")
+                dist.all_gather_into_tensor(Rst, Rl)
+                _lib.check(L.pl_tsqr_svd_f64(Wst.data_ptr(), Sd.data_ptr(), Vd.data_ptr(), Rst.data_ptr(), size * n, n, wp2, wb2,
+                                             _dev.stream()), "pl_tsqr_svd_f64")
+                host_S.copy_(Sd); host_V.copy_(Vd)           # synchronises the torch stream: W is ready
+                _lib.check(L.pl_tsqr_host_apply_f64(host_U.data_ptr(), Wst[rank * n:(rank + 1) * n].data_ptr(), m_e2e, n),
+                           "pl_tsqr_host_apply_f64")
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -318,7 +328,7 @@ def run_ours(args):
                "h2d_bytes_per_step": m_e2e * n * 8, "d2h_bytes_per_step": m_e2e * n * 8 + n * 8 + n * n * 8,
                "rows_per_gpu": m_e2e, "ms_per_step": dt * 1e3,
                "path": "pl_tsqr_svd_host_f64 (host pointers; row-chunk pipeline H2D || factor+Q, GEMM || D2H inside the timed region, device buffers cached by the library after the warm-up call)" if size == 1
-                       else "pyloworder_b200.math.tsqr_svd on pinned host tensors (H2D + compute + D2H inside the timed region)"}
+                       else "pl_tsqr_host_factor_f64 -> NCCL all-gather of R -> pl_tsqr_svd_f64 on the stack -> pl_tsqr_host_apply_f64 (host pointers; chunked H2D / D2H inside the timed region)"}
         if size == 1 and m_e2e == m:
             e2e["s_rel_diff_vs_device_path"] = float((host_S - S_dev).abs().max() / S_dev[0])
     except Exception as ex:  # host memory too small etc.

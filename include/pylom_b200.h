@@ -115,6 +115,17 @@ int pl_pod_run_inplace_f64(double* Ubuf, double* S, double* VT, double* X_mean, 
 /* Same signature and meaning as the reference's dtsqr_svd but HOST pointers (what a ctypes / Cython
  * binding of the reference would pass): allocates device memory, copies in, computes, copies back. */
 int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n);
+/* P ranks from host memory.  The reference's dtsqr_svd is collective (MPI inside, svd.c:602-669); here the exchange
+ * stays with the caller so that any transport works:
+ *   pl_tsqr_host_factor_f64(R, Ai, m_i, n)      local phase: chunked H2D || factorisation, R (n x n) out
+ *   all-gather the P matrices R (MPI_Allgather / ncclAllGather)  ->  Rstack (P n x n)
+ *   pl_tsqr_host_stack_f64(Wstack, S, VT, Rstack, P, n)   SVD of the stack: Wstack (P n x n) = Q2 Ur, S, VT
+ *   pl_tsqr_host_apply_f64(Ui, Wstack + rank n n, m_i, n)   Ui = Q1_i W, chunked GEMM || D2H
+ * R, Rstack, Wstack, S, VT and W may be host or device pointers; Ai / Ui are host pointers.  State is kept between the two calls
+ * (one factorisation in flight per process). */
+int pl_tsqr_host_factor_f64(double* R, const double* Ai, int64_t m, int64_t n);
+int pl_tsqr_host_stack_f64(double* Wstack, double* S, double* VT, const double* Rstack, int64_t P, int64_t n);
+int pl_tsqr_host_apply_f64(double* Ui, const double* W, int64_t m, int64_t n);
 /* the host entry point keeps its device buffers between calls (grow-only); this releases them */
 void pl_host_cache_free(void);
 

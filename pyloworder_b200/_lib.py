@@ -42,6 +42,9 @@ _SIGS = {
     "pl_pod_run_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
     "pl_reconstruct_f64": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "pl_tsqr_svd_host_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "pl_tsqr_host_factor_f64": (_int, [_vp, _vp, _i64, _i64]),
+    "pl_tsqr_host_stack_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "pl_tsqr_host_apply_f64": (_int, [_vp, _vp, _i64, _i64]),
     "pl_host_cache_free": (None, []),
     "pl_profile_enable": (None, [_int]),
     "pl_profile_read": (_int, [_vp, _vp, _int]),

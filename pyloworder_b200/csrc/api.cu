@@ -393,13 +393,53 @@ static int host_chunks(int64_t m, int64_t n) {
   return c < 1 ? 1 : (int)c;
 }
 
-// Host-pointer TSQR-SVD (replaces dtsqr_svd, pyLOM/vmmath/src/svd.c:~1390, for one rank).  The rows are processed as
-// C chunks, i.e. as a two-level TSQR on one device, so that PCIe and the GPU work at the same time:
-//   H2D(c+1)            ||  factor(c), R_c, explicit Q_c            (copy stream / compute stream)
-//   QR of the stacked R_c, Jacobi SVD, B = Q_stack Ur               (side stream, next to the last chunk's Q_c)
-//   U_c = Q_c B_c (GEMM) ||  D2H(c-1)                               (ping-pong output buffers)
-int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
-  PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
+// Host-pointer TSQR-SVD (replaces dtsqr_svd, pyLOM/vmmath/src/svd.c:678-712).  The rows are processed as C chunks,
+// i.e. as a two-level TSQR on one device, so that PCIe and the GPU work at the same time:
+//   factor:  H2D(c+1)   ||  factor(c), R_c, explicit Q_c             (copy stream / compute stream)
+//            QR of the stacked R_c -> this rank's R                   (side stream, beside the last chunk's Q_c)
+//   [single rank: Jacobi SVD of R on the side stream; P ranks: the caller exchanges the R's and provides W]
+//   apply:   B = Q_stack W;  U_c = Q_c B_c (GEMM)  ||  D2H(c-1)       (ping-pong output buffers)
+// The state between the two phases (chunk plans, device buffers) lives in g_hs.
+struct HostChunk { int64_t r0, rows; Plan P; size_t vb, tws, vup, vpiv; };
+static struct HostState {
+  bool valid = false;
+  int64_t m = 0, n = 0, kp = 0, np = 0, m2 = 0;
+  int C = 0;
+  size_t chunk_out = 0, o_rs = 0, o_bs = 0, o_r2 = 0, o_ur = 0, o_bp = 0, o_svd = 0, o_ws2 = 0, o_w = 0;
+  std::vector<HostChunk> ch;
+  WsLayout L2;
+  void *dVb = nullptr, *dOut = nullptr, *dS = nullptr, *dV = nullptr, *aux = nullptr;
+  cudaStream_t st = nullptr, cs = nullptr, s2 = nullptr;   // compute / copy / small-factor streams
+  cudaEvent_t eR = nullptr, eB = nullptr;
+} g_hs;
+
+static int host_streams() {
+  HostState& H = g_hs;
+  if (H.st) return 0;
+  int lo = 0, hi = 0;
+  PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  PL_CUDA(cudaStreamCreateWithFlags(&H.st, cudaStreamNonBlocking));
+  PL_CUDA(cudaStreamCreateWithFlags(&H.cs, cudaStreamNonBlocking));
+  PL_CUDA(cudaStreamCreateWithPriority(&H.s2, cudaStreamNonBlocking, hi));
+  PL_CUDA(cudaEventCreateWithFlags(&H.eR, cudaEventDisableTiming));
+  PL_CUDA(cudaEventCreateWithFlags(&H.eB, cudaEventDisableTiming));
+  return 0;
+}
+
+struct EventList {
+  std::vector<cudaEvent_t> e;
+  int init(int k) {
+    e.resize(k);
+    for (auto& x : e) PL_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    return 0;
+  }
+  ~EventList() { for (auto x : e) if (x) cudaEventDestroy(x); }
+};
+
+// Phase 1.  Leaves this rank's R (n x n) in the device buffer at o_r2, enqueued on stream s2 (not synchronised).
+static int host_factor(const double* Ai, int64_t m, int64_t n) {
+  HostState& H = g_hs;
+  H.valid = false;
   int C = host_chunks(m, n);
   const int64_t npad = round_up(n, NB);
   const bool direct = (npad == n);                       // rows land in the factorisation buffer as they are
@@ -407,12 +447,12 @@ int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, in
   C = (int)((m + mc - 1) / mc);
   if (C > 1 && m - (int64_t)(C - 1) * mc < 4 * n) C--;   // ... and absorbs a remainder that would be too short
   if (C == 1) mc = m;
-  struct Chunk { int64_t r0, rows; Plan P; size_t vb, tws, vup, vpiv; };
-  std::vector<Chunk> ch(C);
+  H.m = m; H.n = n; H.C = C;
+  H.ch.assign(C, HostChunk());
   size_t vb_bytes = 0, aux_bytes = 0;
   int64_t max_rows = 0;
   for (int c = 0; c < C; c++) {
-    Chunk& k = ch[c];
+    HostChunk& k = H.ch[c];
     k.r0 = (int64_t)c * mc; k.rows = (c == C - 1) ? m - k.r0 : mc;
     if (k.rows < n) { set_error("host pipeline: chunk %d has %lld rows < n", c, (long long)k.rows); return -5; }
     k.P = make_plan(k.rows, n);
@@ -422,101 +462,164 @@ int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, in
     k.vpiv = aux_bytes; aux_bytes += al((size_t)k.P.vpiv_strips * NB * NB * 8);
     if (k.rows > max_rows) max_rows = k.rows;
   }
-  // small buffers: stacked R (C n x n), B = Q_stack Ur (C n x n), R2, Ur, packed B chunk, Jacobi scratch, level-2 workspace
-  const int64_t kp = round_up(n, 16), np = round_up(n, 64);
-  const int64_t m2 = (int64_t)C * n;
-  WsLayout L2 = make_layout(m2, n);
+  // small buffers: stacked R (C n x n), B = Q_stack W (C n x n), R2, Ur, W, packed B chunk, Jacobi scratch, level-2 workspace
+  H.kp = round_up(n, 16); H.np = round_up(n, 64); H.m2 = (int64_t)C * n;
+  H.L2 = make_layout(H.m2, n);
   size_t off = aux_bytes;
-  const size_t o_rs = off;  off += al((size_t)m2 * n * 8);
-  const size_t o_bs = off;  off += al((size_t)m2 * n * 8);
-  const size_t o_r2 = off;  off += al((size_t)n * n * 8);
-  const size_t o_ur = off;  off += al((size_t)n * n * 8);
-  const size_t o_bp = off;  off += al((size_t)kp * np * 8);
-  const size_t o_svd = off; off += al((size_t)svd_small_scratch_doubles(n) * 8);
-  const size_t o_ws2 = off; off += C > 1 ? L2.total : 0;
-  void *dVb = nullptr, *dOut = nullptr, *dS = nullptr, *dV = nullptr, *aux = nullptr, *stage = nullptr;
-  const size_t chunk_out = al((size_t)max_rows * n * 8);
+  H.o_rs = off;  off += al((size_t)H.m2 * n * 8);
+  H.o_bs = off;  off += al((size_t)H.m2 * n * 8);
+  H.o_r2 = off;  off += al((size_t)n * n * 8);
+  H.o_ur = off;  off += al((size_t)n * n * 8);
+  H.o_w = off;   off += al((size_t)n * n * 8);
+  H.o_bp = off;  off += al((size_t)H.kp * H.np * 8);
+  H.o_svd = off; off += al((size_t)svd_small_scratch_doubles(n) * 8);
+  H.o_ws2 = off; off += C > 1 ? H.L2.total : 0;
+  H.chunk_out = al((size_t)max_rows * n * 8);
+  void* stage = nullptr;
   int rc;
-  if ((rc = hc_get(0, vb_bytes, &dVb)) || (rc = hc_get(1, 2 * chunk_out, &dOut)) || (rc = hc_get(2, (size_t)n * 8, &dS)) ||
-      (rc = hc_get(3, (size_t)n * n * 8, &dV)) || (rc = hc_get(4, off, &aux)) ||
-      (!direct && (rc = hc_get(5, 2 * chunk_out, &stage)))) { pl_host_cache_free(); return rc; }
-  static cudaStream_t st = nullptr, cs = nullptr, s2 = nullptr;   // compute / copy / small-factor streams
-  static cudaEvent_t eR = nullptr, eB = nullptr;
-  if (!st) {
-    int lo = 0, hi = 0;
-    PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    PL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    PL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    PL_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
-    PL_CUDA(cudaEventCreateWithFlags(&eR, cudaEventDisableTiming));
-    PL_CUDA(cudaEventCreateWithFlags(&eB, cudaEventDisableTiming));
-  }
-  std::vector<cudaEvent_t> ev(C), evs(2), evd(2);
-  for (auto* v : {&ev, &evs, &evd}) for (auto& e : *v) PL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  struct EvGuard { std::vector<cudaEvent_t>*a, *b, *c; ~EvGuard() { for (auto* v : {a, b, c}) for (auto e : *v) cudaEventDestroy(e); } }
-      guard{&ev, &evs, &evd};
-  double* Rs = at(aux, o_rs);
-  double* Bs = at(aux, o_bs);
-  double* R2 = at(aux, o_r2);
-  double* Ur = at(aux, o_ur);
-  double* Bp = at(aux, o_bp);
-  // ---- phase 1: chunks arrive, get factored and turned into explicit Q_c while the next chunk is on the wire
+  if ((rc = hc_get(0, vb_bytes, &H.dVb)) || (rc = hc_get(1, 2 * H.chunk_out, &H.dOut)) || (rc = hc_get(2, (size_t)n * 8, &H.dS)) ||
+      (rc = hc_get(3, (size_t)n * n * 8, &H.dV)) || (rc = hc_get(4, off, &H.aux)) ||
+      (!direct && (rc = hc_get(5, 2 * H.chunk_out, &stage)))) { pl_host_cache_free(); return rc; }
+  if ((rc = host_streams())) return rc;
+  EventList ev, evs;
+  if ((rc = ev.init(C)) || (rc = evs.init(2))) return rc;
+  cudaStream_t st = H.st, cs = H.cs, s2 = H.s2;
+  double* Rs = at(H.aux, H.o_rs);
+  double* R2 = at(H.aux, H.o_r2);
+  // chunks arrive, get factored and turned into explicit Q_c while the next chunk is on the wire
   for (int c = 0; c < C; c++) {
-    Chunk& k = ch[c];
-    double* Vb = at(dVb, k.vb);
+    HostChunk& k = H.ch[c];
+    double* Vb = at(H.dVb, k.vb);
     const size_t bytes = (size_t)k.rows * n * 8;
     if (direct) {
       PL_CUDA(cudaMemcpyAsync(Vb, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
-      PL_CUDA(cudaEventRecord(ev[c], cs));
-      PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+      PL_CUDA(cudaEventRecord(ev.e[c], cs));
+      PL_CUDA(cudaStreamWaitEvent(st, ev.e[c], 0));
     } else {
-      double* sg = reinterpret_cast<double*>(static_cast<char*>(stage) + (size_t)(c & 1) * chunk_out);
-      if (c >= 2) PL_CUDA(cudaStreamWaitEvent(cs, evs[c & 1], 0));           // staging buffer consumed
+      double* sg = reinterpret_cast<double*>(static_cast<char*>(stage) + (size_t)(c & 1) * H.chunk_out);
+      if (c >= 2) PL_CUDA(cudaStreamWaitEvent(cs, evs.e[c & 1], 0));         // staging buffer consumed
       PL_CUDA(cudaMemcpyAsync(sg, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
-      PL_CUDA(cudaEventRecord(ev[c], cs));
-      PL_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+      PL_CUDA(cudaEventRecord(ev.e[c], cs));
+      PL_CUDA(cudaStreamWaitEvent(st, ev.e[c], 0));
       if ((rc = copy_pad(Vb, k.P.npad, sg, n, k.rows, n, k.P.npad, st))) return rc;
-      PL_CUDA(cudaEventRecord(evs[c & 1], st));
+      PL_CUDA(cudaEventRecord(evs.e[c & 1], st));
     }
     PL_CUDA(cudaMemsetAsync(Vb + (size_t)k.rows * k.P.npad, 0, (size_t)(k.P.mrows - k.rows) * k.P.npad * 8, st));
-    if ((rc = caqr_factor(k.P, Vb, at(aux, k.tws), at(aux, k.vup), at(aux, k.vpiv), st))) return rc;
+    if ((rc = caqr_factor(k.P, Vb, at(H.aux, k.tws), at(H.aux, k.vup), at(H.aux, k.vpiv), st))) return rc;
     if ((rc = caqr_extract_r(k.P, Vb, C > 1 ? Rs + (size_t)c * n * n : R2, n, st))) return rc;
-    if (c == C - 1) PL_CUDA(cudaEventRecord(eR, st));
-    if ((rc = caqr_form_q(k.P, Vb, at(aux, k.tws), at(aux, k.vup), at(aux, k.vpiv), st))) return rc;
+    if (c == C - 1) PL_CUDA(cudaEventRecord(H.eR, st));
+    if ((rc = caqr_form_q(k.P, Vb, at(H.aux, k.tws), at(H.aux, k.vup), at(H.aux, k.vpiv), st))) return rc;
   }
-  // ---- phase 2 (side stream, beside the last chunk's Q formation): stacked-R QR, Jacobi SVD, B = Q_stack Ur
-  PL_CUDA(cudaStreamWaitEvent(s2, eR, 0));
-  const double* B = Ur;
+  // side stream, beside the last chunk's Q formation: QR of the stacked R_c
+  PL_CUDA(cudaStreamWaitEvent(s2, H.eR, 0));
   if (C > 1) {
-    void* ws2 = static_cast<char*>(aux) + o_ws2;
-    if ((rc = qr_factor(R2, nullptr, Rs, m2, n, 0, ws2, L2, s2))) return rc;
+    void* ws2 = static_cast<char*>(H.aux) + H.o_ws2;
+    if ((rc = qr_factor(R2, nullptr, Rs, H.m2, n, 0, ws2, H.L2, s2))) return rc;
   }
-  if ((rc = svd_small(Ur, n, (double*)dS, (double*)dV, n, R2, n, n, at(aux, o_svd), nullptr, s2))) return rc;
+  H.valid = true;      // (events still pending are released by the runtime when they complete)
+  return 0;
+}
+
+// Phase 2.  Wd: device n x n matrix, ready on stream s2.  Ui (host) = Q_local Wd.
+static int host_apply(double* Ui, const double* Wd) {
+  HostState& H = g_hs;
+  if (!H.valid) { set_error("host pipeline: apply without a preceding factor call"); return -1; }
+  H.valid = false;
+  const int64_t n = H.n;
+  const int C = H.C;
+  cudaStream_t st = H.st, cs = H.cs, s2 = H.s2;
+  int rc;
+  EventList ev, evd;
+  if ((rc = ev.init(C)) || (rc = evd.init(2))) return rc;
+  const double* B = Wd;
   if (C > 1) {
-    void* ws2 = static_cast<char*>(aux) + o_ws2;
-    if ((rc = qr_apply_q(Bs, n, Ur, n, n, m2, n, 0, ws2, L2, s2))) return rc;
+    void* ws2 = static_cast<char*>(H.aux) + H.o_ws2;
+    double* Bs = at(H.aux, H.o_bs);
+    if ((rc = qr_apply_q(Bs, n, Wd, n, n, H.m2, n, 0, ws2, H.L2, s2))) return rc;
     B = Bs;
   }
-  PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, s2));
-  PL_CUDA(cudaMemcpyAsync(VT, dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s2));
-  PL_CUDA(cudaEventRecord(eB, s2));
-  PL_CUDA(cudaStreamWaitEvent(st, eB, 0));
-  // ---- phase 3: U_c = Q_c B_c; the D2H of a chunk overlaps the GEMM of the next one
+  PL_CUDA(cudaEventRecord(H.eB, s2));
+  PL_CUDA(cudaStreamWaitEvent(st, H.eB, 0));
+  double* Bp = at(H.aux, H.o_bp);
+  // U_c = Q_c B_c; the D2H of a chunk overlaps the GEMM of the next one
   for (int c = 0; c < C; c++) {
-    Chunk& k = ch[c];
-    double* out = reinterpret_cast<double*>(static_cast<char*>(dOut) + (size_t)(c & 1) * chunk_out);
-    if (c >= 2) PL_CUDA(cudaStreamWaitEvent(st, evd[c & 1], 0));             // output buffer drained
-    if ((rc = pad_small(Bp, kp, np, B + (size_t)c * n * n, n, n, n, nullptr, st))) return rc;
-    if ((rc = gemm_tall(out, n, at(dVb, k.vb), k.P.npad, Bp, np, k.rows, n, kp, st))) return rc;
-    PL_CUDA(cudaEventRecord(ev[c], st));
-    PL_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
+    HostChunk& k = H.ch[c];
+    double* out = reinterpret_cast<double*>(static_cast<char*>(H.dOut) + (size_t)(c & 1) * H.chunk_out);
+    if (c >= 2) PL_CUDA(cudaStreamWaitEvent(st, evd.e[c & 1], 0));           // output buffer drained
+    if ((rc = pad_small(Bp, H.kp, H.np, B + (size_t)c * n * n, n, n, n, nullptr, st))) return rc;
+    if ((rc = gemm_tall(out, n, at(H.dVb, k.vb), k.P.npad, Bp, H.np, k.rows, n, H.kp, st))) return rc;
+    PL_CUDA(cudaEventRecord(ev.e[c], st));
+    PL_CUDA(cudaStreamWaitEvent(cs, ev.e[c], 0));
     PL_CUDA(cudaMemcpyAsync(Ui + k.r0 * n, out, (size_t)k.rows * n * 8, cudaMemcpyDeviceToHost, cs));
-    PL_CUDA(cudaEventRecord(evd[c & 1], cs));
+    PL_CUDA(cudaEventRecord(evd.e[c & 1], cs));
   }
   PL_CUDA(cudaStreamSynchronize(s2));
   PL_CUDA(cudaStreamSynchronize(st));
   PL_CUDA(cudaStreamSynchronize(cs));
   return 0;
+}
+
+int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
+  PL_ARG(n > 0 && m >= n, 5, "need m >= n > 0");
+  int rc = host_factor(Ai, m, n);
+  if (rc) return rc;
+  HostState& H = g_hs;
+  double* Ur = at(H.aux, H.o_ur);
+  if ((rc = svd_small(Ur, n, (double*)H.dS, (double*)H.dV, n, at(H.aux, H.o_r2), n, n, at(H.aux, H.o_svd), nullptr, H.s2))) return rc;
+  PL_CUDA(cudaMemcpyAsync(S, H.dS, (size_t)n * 8, cudaMemcpyDeviceToHost, H.s2));
+  PL_CUDA(cudaMemcpyAsync(VT, H.dV, (size_t)n * n * 8, cudaMemcpyDeviceToHost, H.s2));
+  return host_apply(Ui, Ur);
+}
+
+// P ranks: the reference's dtsqr_svd is collective (MPI inside, svd.c:602-669).  Here the exchange stays with the
+// caller:  factor (local)  ->  all-gather of the n x n R's (MPI / NCCL)  ->  SVD of the (P n) x n stack, e.g. with
+// pl_tsqr_svd_host_f64 / pl_tsqr_svd_f64, giving W_stack = Q2 Ur, S, VT  ->  apply with W = rows [rank n, (rank+1) n).
+// R and W may be host or device pointers (unified addressing).
+int pl_tsqr_host_factor_f64(double* R, const double* Ai, int64_t m, int64_t n) {
+  PL_ARG(n > 0 && m >= n, 4, "need m >= n > 0");
+  PL_ARG(R != nullptr, 1, "R is NULL");
+  int rc = host_factor(Ai, m, n);
+  if (rc) return rc;
+  HostState& H = g_hs;
+  PL_CUDA(cudaMemcpyAsync(R, at(H.aux, H.o_r2), (size_t)n * n * 8, cudaMemcpyDefault, H.s2));
+  PL_CUDA(cudaStreamSynchronize(H.s2));        // R is ready; the last chunk's Q formation keeps running on the compute stream
+  return 0;
+}
+// SVD of the gathered stack between the two phases: Wstack (P n x n) = Q2 Ur, S, VT.  Uses its own small device
+// buffers (not the cached pipeline state, which holds the factorisation in flight).  Host or device pointers.
+int pl_tsqr_host_stack_f64(double* Wstack, double* S, double* VT, const double* Rstack, int64_t P, int64_t n) {
+  PL_ARG(P >= 1 && n > 0, 5, "need P >= 1, n > 0");
+  PL_ARG(Wstack && S && VT && Rstack, 1, "NULL pointer");
+  int rc = host_streams();
+  if (rc) return rc;
+  const int64_t m2 = P * n;
+  const size_t mat = al((size_t)m2 * n * 8), sq = al((size_t)n * n * 8), wsb = pl_qr_workspace_bytes(m2, n);
+  char* buf = nullptr;
+  cudaError_t e = cudaMalloc(&buf, 2 * mat + sq + al((size_t)n * 8) + wsb + 256);
+  if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return 1000 + (int)e; }
+  double* dR = reinterpret_cast<double*>(buf);
+  double* dW = reinterpret_cast<double*>(buf + mat);
+  double* dVt = reinterpret_cast<double*>(buf + 2 * mat);
+  double* dS = reinterpret_cast<double*>(buf + 2 * mat + sq);
+  void* ws = buf + 2 * mat + sq + al((size_t)n * 8);
+  cudaStream_t s = g_hs.s2;
+  rc = (int)cudaMemcpyAsync(dR, Rstack, (size_t)m2 * n * 8, cudaMemcpyDefault, s);
+  if (!rc) rc = tsqr_svd_impl(dW, dS, dVt, nullptr, dR, m2, n, 0, ws, wsb, s);
+  if (!rc) rc = (int)cudaMemcpyAsync(Wstack, dW, (size_t)m2 * n * 8, cudaMemcpyDefault, s);
+  if (!rc) rc = (int)cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDefault, s);
+  if (!rc) rc = (int)cudaMemcpyAsync(VT, dVt, (size_t)n * n * 8, cudaMemcpyDefault, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(buf);
+  if (!rc && e2 != cudaSuccess) { set_error("CUDA error: %s", cudaGetErrorString(e2)); rc = 1000 + (int)e2; }
+  return rc;
+}
+int pl_tsqr_host_apply_f64(double* Ui, const double* W, int64_t m, int64_t n) {
+  HostState& H = g_hs;
+  PL_ARG(H.valid && m == H.m && n == H.n, 3, "apply must follow pl_tsqr_host_factor_f64 with the same m, n");
+  PL_ARG(Ui != nullptr && W != nullptr, 1, "NULL pointer");
+  double* Wd = at(H.aux, H.o_w);
+  PL_CUDA(cudaMemcpyAsync(Wd, W, (size_t)n * n * 8, cudaMemcpyDefault, H.s2));
+  return host_apply(Ui, Wd);
 }
 
 }  // extern "C"

@@ -89,6 +89,39 @@ for (m, n, r) in ((6000, 48, 8),):
     ok &= bool(good)
     if rank == 0:
         print(f"P={size} DMD {m}x{n} r={r}: mu_abs={dmu:.2e} mode_amp_rel={float(dpb):.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+# ---- host-pointer phase calls: factor (chunked H2D || QR) -> NCCL all-gather of R -> stack SVD -> apply (GEMM || D2H)
+from pyloworder_b200 import _lib
+L = _lib.lib()
+os.environ["PL_HOST_CHUNKS"] = "3"
+for (m, n) in ((30000, 64), (9000, 33)):
+    X = synth.snapshots(m, n, 2024)
+    shards = [X[slice(*po.worksplit(0, m, k, size))] for k in range(size)]
+    Xi = np.ascontiguousarray(shards[rank]); mi = Xi.shape[0]
+    Rl = torch.empty((n, n), dtype=torch.float64, device=dev)
+    Rst = torch.empty((size * n, n), dtype=torch.float64, device=dev); Wst = torch.empty_like(Rst)
+    Sd = torch.empty(n, dtype=torch.float64, device=dev); Vd = torch.empty((n, n), dtype=torch.float64, device=dev)
+    Uh = np.zeros((mi, n))
+    rc = L.pl_tsqr_host_factor_f64(Rl.data_ptr(), Xi.ctypes.data, mi, n)
+    dist.all_gather_into_tensor(Rst, Rl)
+    torch.cuda.synchronize()
+    rc |= L.pl_tsqr_host_stack_f64(Wst.data_ptr(), Sd.data_ptr(), Vd.data_ptr(), Rst.data_ptr(), size, n)
+    rc |= L.pl_tsqr_host_apply_f64(Uh.ctypes.data, Wst[rank * n:(rank + 1) * n].data_ptr(), mi, n)
+    Uo, So, Vo = po.tsqr_svd(shards)
+    Sh, Vh = Sd.cpu().numpy(), Vd.cpu().numpy()
+    sig = np.abs(Sh - So).max() / So[0]
+    keep = (So / So[0] >= 1e-8)
+    gaps = np.minimum(np.r_[np.inf, -np.diff(So)], np.r_[-np.diff(So), np.inf]) / So[0] >= 1e-6
+    sel = keep & gaps
+    ip = torch.from_numpy(np.einsum("ik,ik->k", Uo[rank], Uh)).to(dev)
+    dist.all_reduce(ip)
+    ipn = np.abs(ip.cpu().numpy())
+    G = torch.from_numpy(Uh.T @ Uh).to(dev)
+    dist.all_reduce(G)
+    orth = float((G - torch.eye(n, dtype=torch.float64, device=dev)).abs().max())
+    good = rc == 0 and sig <= 1e-10 and ipn[sel].min() >= 1 - 1e-8 and orth <= 1e-12
+    ok &= bool(good)
+    if rank == 0:
+        print(f"P={size} host phase calls {m}x{n}: rc={rc} sigma_rel={sig:.2e} mode_min={ipn[sel].min():.12f} orth={orth:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)

@@ -266,6 +266,29 @@ def test_c_abi_host_pipeline_chunked(pl, monkeypatch, m, n, chunks):
     L.pl_host_cache_free()
 
 
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_c_abi_host_phase_calls(pl, monkeypatch, chunks):
+    """The multi-rank host recipe (factor -> exchange of R -> stack SVD -> apply) run for one rank with HOST pointers
+    for every argument, and the misuse cases (apply without factor, mismatched sizes)."""
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    monkeypatch.setenv("PL_HOST_CHUNKS", str(chunks))
+    m, n = 12000, 40
+    A = synth.snapshots(m, n, 77)
+    R = np.zeros((n, n)); W = np.zeros((n, n)); S = np.zeros(n); V = np.zeros((n, n)); U = np.zeros((m, n))
+    assert L.pl_tsqr_host_apply_f64(U.ctypes.data, W.ctypes.data, m, n) != 0          # nothing factored yet
+    assert L.pl_tsqr_host_factor_f64(R.ctypes.data, A.ctypes.data, m, n) == 0, L.pl_last_error()
+    assert np.allclose(np.tril(R, -1), 0)
+    Sa = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(np.linalg.svd(R, compute_uv=False) - Sa).max() <= 1e-13 * Sa[0]     # R^T R = A^T A
+    assert L.pl_tsqr_host_stack_f64(W.ctypes.data, S.ctypes.data, V.ctypes.data, R.ctypes.data, 1, n) == 0, L.pl_last_error()
+    assert L.pl_tsqr_host_apply_f64(U.ctypes.data, W.ctypes.data, m + 1, n) != 0      # wrong size is refused ...
+    assert L.pl_tsqr_host_apply_f64(U.ctypes.data, W.ctypes.data, m, n) == 0, L.pl_last_error()   # ... and the state survives
+    assert_svd_parity(po.tsqr_svd(A), (U, S, V))
+    assert L.pl_tsqr_host_apply_f64(U.ctypes.data, W.ctypes.data, m, n) != 0          # consumed
+    L.pl_host_cache_free()
+
+
 @pytest.mark.parametrize("m,a,b", [(5000, 16, 64), (5000, 64, 16), (40000, 8, 512), (33333, 33, 151), (20000, 151, 151),
                                     (3001, 24, 40), (70, 5, 9), (100000, 200, 96), (17, 64, 64), (250000, 12, 999)])
 def test_matmul_tn_kernel(pl, m, a, b):

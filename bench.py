@@ -283,16 +283,27 @@ def run_ours(args):
     S_dev = S.cpu() if size == 1 else None
     del S, V
     # host memory: 2 pinned buffers of m_e2e x n per rank; with several ranks on one node the e2e sample is capped
-    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else 2_000_000)
+    e2e_rows = args.e2e_rows if args.e2e_rows > 0 else (ROWS_PER_GPU if size == 1 else (2_000_000 if size <= 4 else 1_000_000))
     m_e2e = min(m, e2e_rows)
+    alloc_err = None
     try:
         host_in = torch.empty((m_e2e, n), dtype=torch.float64, pin_memory=True)
         host_in.copy_(A[:m_e2e])
         host_U = torch.empty((m_e2e, n), dtype=torch.float64, pin_memory=True)
         host_S = torch.empty(n, dtype=torch.float64); host_V = torch.empty((n, n), dtype=torch.float64)
-        del A
-        _dev.free_workspaces()
-        torch.cuda.empty_cache()
+    except Exception as ex:  # pinned host memory too small
+        alloc_err = str(ex)[:200]
+    del A
+    _dev.free_workspaces()
+    torch.cuda.empty_cache()
+    if size > 1:   # the e2e leg is collective: every rank runs it or none does
+        flag = torch.tensor([1.0 if alloc_err else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag.item()) > 0 and not alloc_err:
+            alloc_err = "pinned host allocation failed on another rank"
+    try:
+        if alloc_err:
+            raise RuntimeError(alloc_err)
         if size == 1:
             def e2e_step():
                 rc = L.pl_tsqr_svd_host_f64(host_U.data_ptr(), host_S.data_ptr(), host_V.data_ptr(), host_in.data_ptr(), m_e2e, n)
@@ -364,7 +375,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
-    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU of the e2e leg (0: full shard on 1 GPU, 1M per GPU otherwise)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU of the e2e leg (0: full shard on 1 GPU, 2M per GPU on 2-4 GPUs, 1M on 8: pinned host memory)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

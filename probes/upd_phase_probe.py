@@ -22,9 +22,14 @@ ms = (ctypes.c_double * 7)(); cnt = (ctypes.c_int64 * 7)()
 L.pl_profile_read(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p), 7)
 print(json.dumps({"update_factor": round(ms[2], 2), "update_formq": round(ms[3], 2), "panel": round(ms[1], 2)}))
 ''' % (ROWS, COLS)
-for flags, label in ((0, "full"), (1, "no staging"), (2, "no GEMM1"), (4, "no T step"), (8, "no GEMM2 (no stores)"), (16, "no stores"),
+ALL = ((0, "full"), (1, "no staging"), (2, "no GEMM1"), (4, "no T step"), (8, "no GEMM2 (no stores)"), (16, "no stores"),
                      (30, "staging only"), (1 | 16, "compute only, no stores"), (1 | 16 | 4 | 8, "GEMM1 only"),
-                     (1 | 16 | 2 | 8, "T step only"), (1 | 16 | 2 | 4, "GEMM2 only"), (1 | 16 | 4, "GEMM1 + GEMM2"), (31, "barriers only")):
+                     (1 | 16 | 2 | 8, "T step only"), (1 | 16 | 2 | 4, "GEMM2 only"), (1 | 16 | 4, "GEMM1 + GEMM2"), (31, "barriers only"),
+                     (64, "full, no L2 prefetch"), (64 | 1 | 16, "compute only, no stores, no prefetch"), (64 | 31, "barriers only, no prefetch"),
+                     (64 | 1 | 16 | 4 | 8, "GEMM1 only, no prefetch"), (64 | 1 | 16 | 2 | 4, "GEMM2 only, no prefetch"), (64 | 1 | 16 | 4, "GEMM1 + GEMM2, no prefetch"),
+                     (32, "full, GEMM1 fragments loaded once"), (32 | 1 | 16 | 4 | 8, "GEMM1 only, fragments loaded once"))
+ONLY = [int(v) for v in os.environ.get("UPD_PROBE_ONLY", "").split(",") if v]
+for flags, label in [fl for fl in ALL if not ONLY or fl[0] in ONLY]:
     env = dict(os.environ, PL_UPD_DBG=str(flags), PL_NO_SVD_OVERLAP="1")
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     print(f"dbg={flags:2d} {label:28s} {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]}", flush=True)

@@ -414,7 +414,7 @@ struct UpdArgs {
   const double* Tl; const double* Vupl; const double* Vpivl; int virt;
   double* C0; int64_t ldc0; int coff0; int nchunk0;
   double* C1; int64_t ldc1; int coff1;
-  int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores
+  int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores, 32 GEMM1 fragments once, 64 no L2 prefetch
 };
 
 // Timing experiments (probes/upd_phase_probe.py): build with -DPL_UPD_EXPERIMENTS and set PL_UPD_DBG to skip phases.
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       cp_async16(&S.Ts[r_lo + 16][c2], tp + 16 * NB, true);
     }
     cp_async_commit();
-    if (it + 1 < cnt) {   // pull the next tile's rows into L2 while this tile computes (128 rows x 256 B each)
+    if (it + 1 < cnt && !UPD_DBG(64)) {   // pull the next tile's rows into L2 while this tile computes (128 rows x 256 B each)
       const int64_t tn = A.forward ? t + 1 : t - 1;
       const int pr = tid >> 1, ph = (tid & 1) * 16;   // row of the tile, 128-byte half of the 256-byte row
       const int pq = pr >> 5, prr = pr & 31;
@@ -514,17 +514,19 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
 #pragma unroll
       for (int q = 0; q < G; q++) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
       const int qn = A.virt ? (first ? 1 : 0) : G;   // virtual-zero input: only the carried block (slab 0 of the first tile) contributes
+      double fa[8], fb[4];
 #pragma unroll
       for (int kk = 0; kk < 2; kk++) {
 #pragma unroll
         for (int q = 0; q < G; q++) {
           if (q >= qn) continue;
           const double (*Cq)[SP] = (q == 0) ? C0 : S.Cs[q];
-          double fa[8], fb[4];
+          if (!UPD_DBG(32) || (q == 0 && kk == 0)) {   // experiment 32: one fragment pair for all 8 MMAs
 #pragma unroll
-          for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16 * kk][16 * mb + g + 8 * (x & 1)];
+            for (int x = 0; x < 8; x++) fa[x] = S.Vs[q][t4 + 4 * (x >> 1) + 16 * kk][16 * mb + g + 8 * (x & 1)];
 #pragma unroll
-          for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16 * kk][8 * ng + g];
+            for (int x = 0; x < 4; x++) fb[x] = Cq[t4 + 4 * x + 16 * kk][8 * ng + g];
+          }
           mma16816(acc[q], fa, fb);
         }
       }

@@ -417,6 +417,24 @@ struct UpdArgs {
   int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores, 32 GEMM1 fragments once, 64 no L2 prefetch
 };
 
+// Per-phase cycle counters of one warp per CTA (build with -DPL_UPD_TIMING[=warp]; read with pl_debug_update_read).
+#ifdef PL_UPD_TIMING
+__device__ unsigned long long g_upd_dbg[8];
+extern "C" int pl_debug_update_read(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_upd_dbg, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_upd_dbg, z, sizeof(z));
+  return 0;
+}
+#define UT_DECL long long ut[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ut_prev = clock64();
+#define UT_MARK(k) do { long long _t = clock64(); ut[k] += _t - ut_prev; ut_prev = _t; } while (0)
+#define UT_FLUSH do { if (lane == 0 && warp == (PL_UPD_TIMING + 0)) { for (int k = 0; k < 8; k++) atomicAdd(&g_upd_dbg[k], (unsigned long long)ut[k]); } } while (0)
+#else
+#define UT_DECL
+#define UT_MARK(k)
+#define UT_FLUSH
+#endif
 // Timing experiments (probes/upd_phase_probe.py): build with -DPL_UPD_EXPERIMENTS and set PL_UPD_DBG to skip phases.
 #ifdef PL_UPD_EXPERIMENTS
 #define UPD_DBG(bit) (A.dbg & (bit))
@@ -458,10 +476,12 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
   const int mb = warp >> 2, ng = warp & 3;     // GEMM1 / T-step: (m16 block, n8 group) of the NB x NB W
   const int gq = warp >> 1, gh = warp & 1;     // GEMM2: (slab, column half)
 
+  UT_DECL
   for (int it = 0; it < cnt; it++) {
     const int i = A.forward ? it : (cnt - 1 - it);
     const int64_t t = t0 + i;
     const bool first = (i == 0);
+    UT_MARK(7);
     // ---- stage V, C, T of this tile
     if (!UPD_DBG(1) || it == 0) {
       const double* vp = vbase + t * v_tile;
@@ -504,8 +524,10 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(vpf));
       }
     }
+    UT_MARK(0);                 // 0: issue of the staging copies + prefetch
     cp_async_wait<0>();
     __syncthreads();
+    UT_MARK(1);                 // 1: wait for the data + barrier
     const double (*C0)[SP] = first ? S.Zs : S.Cs[0];   // slab 0 of the first tile is the carried block
 
     // ---- GEMM1: W = V^T C (+ Z)      four independent accumulator chains (one per slab)
@@ -538,7 +560,9 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       *reinterpret_cast<double2*>(&S.Ws[r + 8][c]) = make_double2(((acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2])) + z23.x,
                                                                    ((acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3])) + z23.y);
     }
+    UT_MARK(2);                 // 2: GEMM1 + epilogue
     __syncthreads();
+    UT_MARK(3);                 // 3: barrier after GEMM1
     // ---- W' = op(T) W     forward: T^T, backward: T
     if (!UPD_DBG(4)) {
       double acc[4] = {0, 0, 0, 0}, accb[4] = {0, 0, 0, 0};
@@ -569,7 +593,9 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
         *reinterpret_cast<double2*>(&S.Zs[r + 8][c]) = z23;
       }
     }
+    UT_MARK(4);                 // 4: T step
     __syncthreads();
+    UT_MARK(5);                 // 5: barrier after the T step
     // ---- GEMM2: C -= V W'     warp -> (slab gq, column half gh)
     if (!UPD_DBG(8)) {
       const bool piv = first && gq == 0;
@@ -609,8 +635,11 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
         }
       }
     }
+    UT_MARK(6);                 // 6: GEMM2 + stores
     __syncthreads();
   }
+  UT_MARK(7);                   // 7: barrier after GEMM2 (+ loop overhead)
+  UT_FLUSH;
   // ---- carried rows back to the pivot block rows
   {
     double* zdst = Cb + (pivrow + r_lo) * ldc + coff + c2;

@@ -72,15 +72,20 @@ static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int6
   const Plan& P = L.plan;
   double* Vb = Vb_ext ? Vb_ext : at(ws, L.vb);
   int rc;
+  // No centering, n a multiple of the panel width, whole row blocks: the first panel's kernels read A directly and the
+  // copy pass (8 + 8 bytes per entry) disappears.  PL_NO_FUSED_INPUT / PL_LOOKAHEAD keep the copy.
+  const bool fused = !center && P.npad == n && (m % NB) == 0 && P.K > 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                     getenv("PL_NO_FUSED_INPUT") == nullptr && getenv("PL_LOOKAHEAD") == nullptr;
   {
     ProfScope ps(PROF_COPY, st);
     if (center == 2) rc = center_var_rows(Vb, P.npad, X_mean, X_var, A, m, n, P.npad, st);
     else if (center) rc = center_rows(Vb, P.npad, X_mean, A, m, n, P.npad, st);
-    else rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
+    else if (!fused) rc = copy_pad(Vb, P.npad, A, n, m, n, P.npad, st);
+    else rc = 0;
     if (rc) return rc;
     PL_CUDA(cudaMemsetAsync(Vb + (size_t)m * P.npad, 0, (size_t)(P.mrows - m) * P.npad * 8, st));
   }
-  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
+  rc = caqr_factor(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st, fused ? A : nullptr);
   if (rc) return rc;
   if (R) rc = caqr_extract_r(P, Vb, R, n, st);
   return rc;

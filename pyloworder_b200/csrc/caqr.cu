@@ -128,7 +128,7 @@ template <int MINB>
 __global__ void __launch_bounds__(160, MINB)
 caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, int64_t nblk, int64_t bs,
                   int64_t ntiles, int s, int upper, double* __restrict__ Tl, double* __restrict__ Vupl,
-                  double* __restrict__ Vpivl) {
+                  double* __restrict__ Vpivl, const double* __restrict__ Asrc) {
   __shared__ __align__(16) double xs[2][5][32];   // pivot column of step j (buffer j&1), pre-published during step j-1
   __shared__ double red[2][5][32];
   __shared__ double prow[2][32];
@@ -144,8 +144,11 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
   double mysc = 0.0;     // 1/(alpha-beta) of column `lane` (every lane owns the bookkeeping of one column)
   PT_DECL
 
+  // Asrc != nullptr (first panel of a factorisation that was not preceded by a copy): the input is read from the
+  // caller's matrix (same leading dimension), everything is written to Vb.
+  const double* Lb = Asrc ? Asrc : Vb;
   if (warp == 0) {   // pivot block -> shared memory (row-wise, coalesced)
-    const double* src = Vb + (row0 + pivblk * bs) * ld + col0 + lane;
+    const double* src = Lb + (row0 + pivblk * bs) * ld + col0 + lane;
 #pragma unroll 8
     for (int r = 0; r < 32; r++) {
       const double v = src[(int64_t)r * ld];
@@ -162,13 +165,15 @@ caqr_panel_kernel(double* __restrict__ Vb, int64_t ld, int64_t row0, int col0, i
     if (warp >= 1) q = (i == 0) ? (warp <= 3 ? warp : -1) : (warp - 1);
     const int64_t kblk = t * G + q;
     const bool valid = (q >= 0) && (kblk < nblk);
-    double* blkp = Vb + (row0 + (valid ? kblk : 0) * bs + 8 * rg) * ld + col0 + cg;
+    const int64_t blko = (row0 + (valid ? kblk : 0) * bs + 8 * rg) * ld + col0 + cg;
+    double* blkp = Vb + blko;
     if (warp >= 1) {
       if (valid) {
+        const double* lp = Lb + blko;
 #pragma unroll
         for (int r = 0; r < 8; r++)
 #pragma unroll
-          for (int ii = 0; ii < 4; ii++) a[ii][r] = blkp[(int64_t)r * ld + 8 * ii];
+          for (int ii = 0; ii < 4; ii++) a[ii][r] = lp[(int64_t)r * ld + 8 * ii];
         if (upper) {
 #pragma unroll
           for (int r = 0; r < 8; r++)
@@ -414,6 +419,7 @@ struct UpdArgs {
   const double* Tl; const double* Vupl; const double* Vpivl; int virt;
   double* C0; int64_t ldc0; int coff0; int nchunk0;
   double* C1; int64_t ldc1; int coff1;
+  const double* Csrc;   // forward pass only: C is READ from here (same ld / offsets), written to C0/C1; nullptr = in place
   int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores, 32 GEMM1 fragments once, 64 no L2 prefetch
 };
 
@@ -463,7 +469,8 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
   const int64_t v_h = upper ? (int64_t)16 * NB : 16 * A.ld;
   const double* vbase = upper ? (A.Vupl + r_lo * NB + c2) : (A.Vb + (A.row0 + r_lo) * A.ld + A.col0 + c2);
   const int64_t c_tile = (int64_t)G * A.bs * ldc, c_q = A.bs * ldc, c_h = 16 * ldc;
-  double* cbase = Cb + (A.row0 + r_lo) * ldc + coff + c2;
+  const double* Lb = A.Csrc ? A.Csrc : Cb;
+  const double* cbase = Lb + (A.row0 + r_lo) * ldc + coff + c2;
   const double* tbase = A.Tl + r_lo * NB + c2;
 
   if (!A.forward) {   // backward: carried rows come from memory
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
     // ---- stage V, C, T of this tile
     if (!UPD_DBG(1) || it == 0) {
       const double* vp = vbase + t * v_tile;
-      double* cp = cbase + t * c_tile;
+      const double* cp = cbase + t * c_tile;
 #pragma unroll
       for (int q = 0; q < G; q++) {
         const bool valid = (t * G + q) < A.nblk;
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
       const int pr = tid >> 1, ph = (tid & 1) * 16;   // row of the tile, 128-byte half of the 256-byte row
       const int pq = pr >> 5, prr = pr & 31;
       if ((tn * G + pq) < A.nblk) {
-        const double* cpf = Cb + (A.row0 + (tn * G + pq) * A.bs + prr) * ldc + coff + ph;
+        const double* cpf = Lb + (A.row0 + (tn * G + pq) * A.bs + prr) * ldc + coff + ph;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(cpf));
         const double* vpf = upper ? (A.Vupl + (tn * TB + pr) * NB + ph)
                                   : (A.Vb + (A.row0 + (tn * G + pq) * A.bs + prr) * A.ld + A.col0 + ph);
@@ -678,7 +685,7 @@ __global__ void set_identity_block_kernel(double* Vb, int64_t ld, int64_t row0, 
 // =============================================================================================
 static int launch_update(const Plan& P, int p, const Level& L, int li, const double* Vb, const double* Tws,
                          const double* Vup, const double* Vpiv, int virt, double* C0, int64_t ldc0, int coff0, int nchunk0, double* C1, int64_t ldc1,
-                         int coff1, int nchunk1, int forward, cudaStream_t st) {
+                         int coff1, int nchunk1, int forward, cudaStream_t st, const double* Csrc = nullptr) {
   if (nchunk0 + nchunk1 <= 0) return 0;
   UpdArgs A;
   A.Vb = Vb; A.ld = P.npad; A.row0 = (int64_t)p * NB; A.col0 = p * NB;
@@ -691,6 +698,7 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   A.dbg = upd_dbg;
   A.C0 = C0; A.ldc0 = ldc0; A.coff0 = coff0; A.nchunk0 = nchunk0;
   A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1;
+  A.Csrc = Csrc;
   static bool attr_set = false;
   if (!attr_set) {
     PL_CUDA(cudaFuncSetAttribute(caqr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
@@ -720,7 +728,7 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
 }
 
 static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb, double* Tws, double* Vup, double* Vpiv,
-                        cudaStream_t st) {
+                        cudaStream_t st, const double* Asrc = nullptr) {
   const int64_t row0 = (int64_t)p * NB; const int col0 = p * NB;
   ProfScope ps(PROF_PANEL, st);
   static const int occ = getenv("PL_PANEL_OCC") ? atoi(getenv("PL_PANEL_OCC")) : 3;
@@ -728,11 +736,11 @@ static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb
   double* Vl = li > 0 ? Vup + L.v_off * (TB * NB) : nullptr;
   double* Pl = li > 0 ? nullptr : Vpiv + L.p_off * (NB * NB);
   if (occ == 4)
-    caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+    caqr_panel_kernel<4><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl, Asrc);
   else if (occ == 2)
-    caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+    caqr_panel_kernel<2><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl, Asrc);
   else
-    caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl);
+    caqr_panel_kernel<3><<<(unsigned)L.nstrips, 160, 0, st>>>(Vb, P.npad, row0, col0, L.nblk, L.bs, L.ntiles, L.s, li > 0, Tl, Vl, Pl, Asrc);
   PL_LAUNCH_CHECK();
   return 0;
 }
@@ -745,7 +753,7 @@ static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb
 // a panel can run back to back before any of its updates).  Measured at 8 M x 512: no gain (622.5 vs 621.6 ms) --
 // two update CTAs fill the register file of an SM (2 x 256 x 128), so a panel CTA only ever replaces an update CTA
 // instead of running beside it.  Off by default; kept for a future update kernel with a smaller footprint.
-int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st) {
+int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st, const double* Asrc) {
   static cudaStream_t ss = nullptr;
   static cudaEvent_t eE = nullptr, eF = nullptr;
   const bool look = P.K > 1 && P.panels[0][0].ntiles >= 2048 && getenv("PL_LOOKAHEAD") != nullptr;
@@ -757,14 +765,18 @@ int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpi
     PL_CUDA(cudaEventCreateWithFlags(&eF, cudaEventDisableTiming));
   }
   int rc;
+  if (Asrc && look) { set_error("caqr_factor: the fused input read is not available with PL_LOOKAHEAD"); return -1; }
   if (!look) {
     for (int p = 0; p < P.K; p++) {
       const int col0 = p * NB;
       const int ntrail = (int)((P.npad - col0 - NB) / NB);
       for (size_t li = 0; li < P.panels[p].size(); li++) {
         const Level& L = P.panels[p][li];
-        if ((rc = launch_panel(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, st))) return rc;
-        rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st);
+        // Asrc: the level-0 kernels of the FIRST panel read the caller's matrix and write Vb -- together they touch
+        // every entry once, which replaces the separate copy pass over A
+        const double* src = (p == 0 && li == 0) ? Asrc : nullptr;
+        if ((rc = launch_panel(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, st, src))) return rc;
+        rc = launch_update(P, p, L, (int)li, Vb, Tws, Vup, Vpiv, 0, nullptr, 0, 0, 0, Vb, P.npad, col0 + NB, ntrail, 1, st, src);
         if (rc) return rc;
       }
     }

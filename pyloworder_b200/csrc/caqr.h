@@ -25,7 +25,9 @@ struct Plan {
 };
 
 Plan make_plan(int64_t m, int64_t n);
-int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st);
+// Asrc (optional): read the input from the caller's row-major matrix with leading dimension P.npad instead of from Vb
+// (needs n == npad and m % NB == 0); Vb then needs no copy of A, only its padding rows zeroed.
+int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st, const double* Asrc = nullptr);
 int caqr_extract_r(const Plan& P, const double* Vb, double* R, int64_t ldr, cudaStream_t st);
 int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, const double* Vpiv, cudaStream_t st);
 

@@ -419,6 +419,40 @@ def test_dmd_against_reference_golden(pl, path):
     assert np.abs(Mc - po.dmd_mode_computation(X, V, S, W)).max() <= 1e-11 * np.abs(Mc).max()
 
 
+def test_fused_input_read_matches(pl, monkeypatch):
+    """n % 32 == 0 and m % 32 == 0 without centering: the first panel reads A directly instead of a padded copy.
+    Same arithmetic, so the results must be bit-identical to the copy path, and A must stay untouched."""
+    for (m, n) in ((64000, 96), (4096, 64), (300_000, 128)):
+        A = dev(synth.snapshots(m, n, 13))
+        A0 = A.clone()
+        U1, S1, V1 = pl.math.tsqr_svd(A)
+        assert torch.equal(A, A0)
+        monkeypatch.setenv("PL_NO_FUSED_INPUT", "1")
+        U0, S0, V0 = pl.math.tsqr_svd(A)
+        monkeypatch.delenv("PL_NO_FUSED_INPUT")
+        assert torch.equal(S0, S1) and torch.equal(V0, V1) and torch.equal(U0, U1)
+        # poison the workspace: nothing of the factorisation buffer may be read before it is written
+        from pyloworder_b200 import _dev
+        for w in _dev._ws_cache.values():
+            w.view(torch.float64)[: w.numel() // 8].fill_(float("nan")) if w.numel() % 8 == 0 else w.fill_(255)
+        U2, S2, V2 = pl.math.tsqr_svd(A)
+        assert torch.equal(S2, S1) and torch.equal(U2, U1)
+
+
+def test_lookahead_schedule_matches(pl, monkeypatch):
+    """The optional two-stream panel look-ahead (PL_LOOKAHEAD=1) reorders launches only: same R, same U."""
+    m, n = 300_000, 96                      # >= 2048 tiles, the size from which the look-ahead engages
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    A = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+    Q0, R0 = pl.math.qr(A)
+    monkeypatch.setenv("PL_LOOKAHEAD", "1")
+    Q1, R1 = pl.math.qr(A)
+    assert torch.equal(R0, R1) and torch.equal(Q0, Q1)
+    I = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert float((Q1.T @ Q1 - I).abs().max()) <= 1e-13
+    assert float((Q1 @ R1 - A).abs().max()) <= 1e-12
+
+
 def test_large_properties(pl):
     """Size-independent properties at a size the CPU oracle would not finish quickly."""
     m, n = 2_000_000, 64

@@ -297,7 +297,8 @@ int pl_svd_f64(double* U, double* S, double* VT, const double* Y, int64_t n, voi
 // explicit Q (which needs the reflectors only); the back-multiply waits for both.  Worth ~1.5 % at 8 M x 512.
 static bool svd_overlap_enabled(int64_t m) {
   static const bool off = getenv("PL_NO_SVD_OVERLAP") != nullptr;
-  return !off && m >= 1000000;
+  static const int64_t min_rows = getenv("PL_SVD_OVERLAP_MIN_ROWS") ? atoll(getenv("PL_SVD_OVERLAP_MIN_ROWS")) : 1000000;
+  return !off && m >= min_rows;
 }
 static int svd_and_apply_overlapped(double* Ui, double* S, double* VT, const double* R, double* Ur, int64_t m, int64_t n,
                                     void* ws, const WsLayout& L, cudaStream_t st, double* Vb_ext) {

@@ -186,6 +186,10 @@ static int tn_launch(const TnCfg& c, double* part, const double* X, int64_t ldx,
 int gemm_tn(double* C, int64_t ldc, const double* X, int64_t ldx, int64_t a, const double* Y, int64_t ldy, int64_t b, int64_t m,
             double* ws, cudaStream_t st) {
   if (a <= 0 || b <= 0) return 0;
+  if (m <= 0) {   // empty contraction: C = 0
+    for (int64_t i = 0; i < a; i++) PL_CUDA(cudaMemsetAsync(C + i * ldc, 0, (size_t)b * 8, st));
+    return 0;
+  }
   int transpose_out = 0;
   if (a > b) {   // the narrow operand goes on the MMA's m side (tile shapes are chosen on it): C^T = Y^T X
     const double* tp = X; X = Y; Y = tp;

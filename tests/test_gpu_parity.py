@@ -314,6 +314,16 @@ def test_matmul_tn_kernel(pl, m, a, b):
     assert isinstance(Cn, np.ndarray) and np.abs(Cn - host(ref)).max() <= tol * max(1.0, float(ref.abs().max()))
 
 
+def test_matmul_tn_degenerate(pl):
+    """Empty contraction (a rank without rows) and 1 x 1 outputs."""
+    from pyloworder_b200.vmmath.maths import matmul_tn
+    X = torch.empty((0, 7), dtype=torch.float64, device="cuda"); Y = torch.empty((0, 5), dtype=torch.float64, device="cuda")
+    C = matmul_tn(X, Y)
+    assert C.shape == (7, 5) and float(C.abs().max()) == 0.0
+    x = torch.arange(1.0, 1001.0, dtype=torch.float64, device="cuda").reshape(-1, 1)
+    assert float(matmul_tn(x, x)[0, 0]) == float((x * x).sum())
+
+
 def test_svd_rectangular(pl):
     """svd() of the wide (r x n) matrix B of randomized_svd and of a local tall matrix, against LAPACK."""
     rng = np.random.default_rng(3)

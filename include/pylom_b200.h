@@ -76,7 +76,9 @@ int pl_qr_factor_var_f64(double* R, double* X_mean, double* X_var, const double*
 /* Second half of dqr (LAPACKE_dorgqr) fused with the back-multiplies of dtsqr/dtsqr_svd
  * (dmatmul at svd.c:673 and svd.c:708):  U(m, nw) = Q1 * W, W (n x nw, ldw) on the device.
  * W == NULL gives U = Q1 (nw must equal n).  Must follow pl_qr_factor_f64 on the same workspace.
- * flags bit 0: Q1 has already been formed in this workspace by an earlier call. */
+ * flags bit 0: Q1 has already been formed in this workspace by an earlier call.
+ * flags bit 1: only form Q1 in the workspace and return (U, W unused) -- lets the caller overlap the Q formation with
+ *              the exchange of the R factors and the small SVD on another stream, then call again with bit 0. */
 int pl_qr_apply_q_f64(double* U, int64_t ldu, const double* W, int64_t ldw, int64_t nw, int64_t m, int64_t n,
                       int flags, void* ws, size_t ws_bytes, void* stream);
 

@@ -100,6 +100,7 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
     rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
     if (rc) return rc;
   }
+  if (flags & 2) return 0;      // form Q1 only; a later call with bit 0 multiplies
   if (!W) {
     if (nw != n) { set_error("apply_q: W == NULL needs nw == n"); return -5; }
     if (U == Vb) return 0;   // explicit Q already in place

@@ -51,6 +51,7 @@ class CudaEngine:
 
     def __init__(self):
         self._ubuf = {}      # tag -> (m + n + 32) x n buffer that holds the reflectors / Q / U of the in-place path
+        self._side = {}      # device -> side stream of the multi-rank path
 
     def factor(self, A, tag, center=False):
         m, n = A.shape
@@ -70,24 +71,48 @@ class CudaEngine:
                        "qr_factor")
         return R, mean
 
-    def apply_q(self, shape, W, tag, device):
+    def form_q(self, shape, tag, device):
+        """Turn the reflectors of the matrix last factored under `tag` into the explicit Q1 (in its workspace);
+        a following apply_q(..., formed=True) only multiplies.  Needs nothing but the local factorisation, so the
+        multi-rank path runs it while the R factors are exchanged and the small SVD is computed on another stream."""
+        m, n = shape
+        L = _lib.lib()
+        ubuf = self._ubuf.get(tag)
+        if ubuf is not None:
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes_inplace(m, n), tag, device)
+            _lib.check(L.pl_qr_apply_q_inplace_f64(ubuf.data_ptr(), 0, 0, m, n, 2, wp, wb, _dev.stream()), "qr_form_q")
+        else:
+            _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, device)
+            _lib.check(L.pl_qr_apply_q_f64(0, n, 0, 0, n, m, n, 2, wp, wb, _dev.stream()), "qr_form_q")
+
+    def apply_q(self, shape, W, tag, device, formed=False):
         """U = Q1 W for the matrix last factored under `tag` (W None -> explicit Q1)."""
         m, n = shape
         L = _lib.lib()
+        flags = 1 if formed else 0
         ubuf = self._ubuf.pop(tag, None)
         if ubuf is not None:
             _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes_inplace(m, n), tag, device)
             if W is not None and (W.shape[0] != n or W.shape[1] != n):
                 raise ValueError("apply_q: W must be n x n")
             ldw = 0 if W is None else W.stride(0)
-            _lib.check(L.pl_qr_apply_q_inplace_f64(ubuf.data_ptr(), _dev.ptr(W), ldw, m, n, 0, wp, wb, _dev.stream()), "qr_apply_q")
+            _lib.check(L.pl_qr_apply_q_inplace_f64(ubuf.data_ptr(), _dev.ptr(W), ldw, m, n, flags, wp, wb, _dev.stream()), "qr_apply_q")
             return ubuf[:m]
         _, wp, wb = _dev.workspace(L.pl_qr_workspace_bytes(m, n), tag, device)
         nw = n if W is None else W.shape[1]
         U = torch.empty((m, nw), dtype=torch.float64, device=device)
         ldw = 0 if W is None else W.stride(0)
-        _lib.check(L.pl_qr_apply_q_f64(U.data_ptr(), nw, _dev.ptr(W), ldw, nw, m, n, 0, wp, wb, _dev.stream()), "qr_apply_q")
+        _lib.check(L.pl_qr_apply_q_f64(U.data_ptr(), nw, _dev.ptr(W), ldw, nw, m, n, flags, wp, wb, _dev.stream()), "qr_apply_q")
         return U
+
+    def side_stream(self, device):
+        """High-priority stream for the exchange + small factorisations of the multi-rank path (None: run in line)."""
+        if os.environ.get("PL_NO_SVD_OVERLAP"):
+            return None
+        s = self._side.get(device)
+        if s is None:
+            s = self._side[device] = torch.cuda.Stream(device=device, priority=-1)
+        return s
 
     def svd(self, R):
         n = R.shape[0]
@@ -153,13 +178,32 @@ def _tsqr_svd_dev(Ad, center=False, engine=None):
         return eng.tsqr_svd_single(Ad, center)
     m, n = Ad.shape
     R_i, mean = eng.factor(Ad, "local", center)
-    cr_start('math.tsqr.allgather')
-    Rstack = eng.allgather_rows(R_i)
-    cr_stop('math.tsqr.allgather')
-    R, _ = eng.factor(Rstack, "stack", False)
-    Ur, S, VT = eng.svd(R)
-    Wfull = eng.apply_q((P * n, n), Ur, "stack", Ad.device)        # Q2 Ur, (P n) x n, tiny
-    U = eng.apply_q((m, n), Wfull[rank * n:(rank + 1) * n], "local", Ad.device)
+
+    def small_part():
+        cr_start('math.tsqr.allgather')
+        Rstack = eng.allgather_rows(R_i)
+        cr_stop('math.tsqr.allgather')
+        R, _ = eng.factor(Rstack, "stack", False)
+        Ur, S, VT = eng.svd(R)
+        return eng.apply_q((P * n, n), Ur, "stack", Ad.device), S, VT        # Q2 Ur, (P n) x n, tiny
+
+    side = eng.side_stream(Ad.device) if hasattr(eng, "side_stream") and m >= 1_000_000 else None
+    if side is None:
+        Wfull, S, VT = small_part()
+        U = eng.apply_q((m, n), Wfull[rank * n:(rank + 1) * n], "local", Ad.device)
+        return U, S, VT, mean
+    # The explicit Q1 needs only the local reflectors: it is formed on the main stream while the all-gather, the QR of
+    # the stack and the latency-bound Jacobi SVD run on a high-priority side stream (same overlap as on one rank).
+    main = torch.cuda.current_stream(Ad.device)
+    side.wait_stream(main)
+    eng.form_q((m, n), "local", Ad.device)
+    with torch.cuda.stream(side):
+        Wfull, S, VT = small_part()
+        R_i.record_stream(side)                  # allocated on the main stream, read on the side stream
+        for t in (Wfull, S, VT):                 # allocated on the side stream, read on the main stream
+            t.record_stream(main)
+    main.wait_stream(side)
+    U = eng.apply_q((m, n), Wfull[rank * n:(rank + 1) * n], "local", Ad.device, formed=True)
     return U, S, VT, mean
 
 

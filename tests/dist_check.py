@@ -11,7 +11,9 @@ import pod_oracle as po, synth
 rank, size = pl.utils.init_distributed("nccl")
 dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
 ok = True
-for (m, n, remove_mean) in ((5000, 24, False), (40000, 151, True), (3001, 64, True), (size * 70, 64, False)):
+# the last case has >= 1 M rows per rank: the explicit Q is formed while exchange + small SVD run on a side stream
+for (m, n, remove_mean) in ((5000, 24, False), (40000, 151, True), (3001, 64, True), (size * 70, 64, False),
+                            (size * 1_000_000, 32, False)):
     X = synth.snapshots(m, n, 2021)
     shards = [X[slice(*po.worksplit(0, m, r, size))] for r in range(size)]
     r0, r1 = pl.utils.worksplit(0, m, rank, size)

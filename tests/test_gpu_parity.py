@@ -449,6 +449,29 @@ def test_fused_input_read_matches(pl, monkeypatch):
         assert torch.equal(S2, S1) and torch.equal(U2, U1)
 
 
+def test_form_q_then_apply_matches(pl):
+    """apply_q in two steps (flags bit 1: form Q only; then bit 0: multiply) -- the split the multi-rank path uses to
+    overlap the Q formation with the exchange -- gives the same U as the one-step call, also on a side stream."""
+    from pyloworder_b200.vmmath.svd import CudaEngine
+    eng = CudaEngine()
+    A = dev(synth.snapshots(50000, 72, 3))
+    W = dev(np.linalg.qr(np.random.default_rng(1).standard_normal((72, 72)))[0])
+    eng.factor(A, "t_one")
+    U1 = eng.apply_q(A.shape, W, "t_one", A.device)
+    R, _ = eng.factor(A, "t_two")
+    eng.form_q(A.shape, "t_two", A.device)
+    side = eng.side_stream(A.device)
+    assert side is not None
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        W2 = W.clone()                       # stands for the small factorisations done on the side stream
+        W2.record_stream(torch.cuda.current_stream(A.device))
+    torch.cuda.current_stream().wait_stream(side)
+    U2 = eng.apply_q(A.shape, W2, "t_two", A.device, formed=True)
+    assert torch.equal(U1, U2)
+    assert float((U2.T @ U2 - torch.eye(72, dtype=torch.float64, device="cuda")).abs().max()) <= 1e-13
+
+
 def test_lookahead_schedule_matches(pl, monkeypatch):
     """The optional two-stream panel look-ahead (PL_LOOKAHEAD=1) reorders launches only: same R, same U."""
     m, n = 300_000, 96                      # >= 2048 tiles, the size from which the look-ahead engages

@@ -128,6 +128,9 @@ int pl_tsqr_svd_host_f64(double* Ui, double* S, double* VT, const double* Ai, in
 int pl_tsqr_host_factor_f64(double* R, const double* Ai, int64_t m, int64_t n);
 int pl_tsqr_host_stack_f64(double* Wstack, double* S, double* VT, const double* Rstack, int64_t P, int64_t n);
 int pl_tsqr_host_apply_f64(double* Ui, const double* W, int64_t m, int64_t n);
+/* row partition the host pipeline uses for an m x n shard (pure host arithmetic; returns the chunk count and fills
+ * rows[0 .. min(count, max_chunks))).  PL_HOST_CHUNKS overrides the target count. */
+int pl_host_chunk_rows(int64_t m, int64_t n, int64_t* rows, int max_chunks);
 /* the host entry point keeps its device buffers between calls (grow-only); this releases them */
 void pl_host_cache_free(void);
 

@@ -45,6 +45,7 @@ _SIGS = {
     "pl_tsqr_host_factor_f64": (_int, [_vp, _vp, _i64, _i64]),
     "pl_tsqr_host_stack_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     "pl_tsqr_host_apply_f64": (_int, [_vp, _vp, _i64, _i64]),
+    "pl_host_chunk_rows": (_int, [_i64, _i64, _vp, _int]),
     "pl_host_cache_free": (None, []),
     "pl_profile_enable": (None, [_int]),
     "pl_profile_read": (_int, [_vp, _vp, _int]),

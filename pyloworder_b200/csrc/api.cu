@@ -400,6 +400,26 @@ static int host_chunks(int64_t m, int64_t n) {
   return c < 1 ? 1 : (int)c;
 }
 
+// Row partition of the host pipeline: C chunks, the first C-1 of `mc` rows (whole 128-row tiles), the last one takes
+// the remainder and is never shorter than 4n rows (it absorbs a short tail).
+static int host_chunk_plan(int64_t m, int64_t n, int64_t* mc_out) {
+  int C = host_chunks(m, n);
+  int64_t mc = round_up((m + C - 1) / C, TB);
+  C = (int)((m + mc - 1) / mc);
+  if (C > 1 && m - (int64_t)(C - 1) * mc < 4 * n) C--;
+  if (C <= 1) { C = 1; mc = m; }
+  *mc_out = mc;
+  return C;
+}
+// exported for the host-logic tests (pure host arithmetic, no device access): rows of every chunk
+int pl_host_chunk_rows(int64_t m, int64_t n, int64_t* rows, int max_chunks) {
+  if (n <= 0 || m < n) return -1;
+  int64_t mc = 0;
+  const int C = host_chunk_plan(m, n, &mc);
+  for (int c = 0; c < C && c < max_chunks; c++) rows[c] = (c == C - 1) ? m - (int64_t)c * mc : mc;
+  return C;
+}
+
 // Host-pointer TSQR-SVD (replaces dtsqr_svd, pyLOM/vmmath/src/svd.c:678-712).  The rows are processed as C chunks,
 // i.e. as a two-level TSQR on one device, so that PCIe and the GPU work at the same time:
 //   factor:  H2D(c+1)   ||  factor(c), R_c, explicit Q_c             (copy stream / compute stream)
@@ -447,13 +467,10 @@ struct EventList {
 static int host_factor(const double* Ai, int64_t m, int64_t n) {
   HostState& H = g_hs;
   H.valid = false;
-  int C = host_chunks(m, n);
+  int64_t mc = 0;
+  const int C = host_chunk_plan(m, n, &mc);
   const int64_t npad = round_up(n, NB);
   const bool direct = (npad == n);                       // rows land in the factorisation buffer as they are
-  int64_t mc = round_up((m + C - 1) / C, TB);            // whole tiles per chunk; the last chunk takes the remainder
-  C = (int)((m + mc - 1) / mc);
-  if (C > 1 && m - (int64_t)(C - 1) * mc < 4 * n) C--;   // ... and absorbs a remainder that would be too short
-  if (C == 1) mc = m;
   H.m = m; H.n = n; H.C = C;
   H.ch.assign(C, HostChunk());
   size_t vb_bytes = 0, aux_bytes = 0;

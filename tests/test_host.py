@@ -33,6 +33,35 @@ def test_workspace_query_and_argument_errors_without_gpu():
     assert rc < 0 and b"workspace" in L.pl_last_error()
 
 
+def test_host_pipeline_row_partition(monkeypatch):
+    """Row chunks of the host-pointer pipeline (pure host arithmetic): they cover the shard exactly, all but the last
+    are equal whole 128-row tiles, none is shorter than 4n rows when there are several, and PL_HOST_CHUNKS is a target,
+    not a promise (the ragged / too-short cases that a first version got wrong)."""
+    from pyloworder_b200 import _lib
+    L = _lib.lib()
+    buf = (ctypes.c_int64 * 64)()
+    rng = np.random.default_rng(0)
+    cases = [(8_000_000, 512, None), (4000, 64, 64), (9001, 33, 7), (20000, 100, 5), (512, 512, 8), (1, 1, 3), (1_000_000, 512, None),
+             (125_000_000, 64, None), (2_000_000, 999, None)]
+    cases += [(int(rng.integers(n, 3_000_000)), n, int(rng.integers(1, 70))) for n in rng.integers(1, 600, size=200).tolist()]
+    for m, n, req in cases:
+        if req is None:
+            monkeypatch.delenv("PL_HOST_CHUNKS", raising=False)
+        else:
+            monkeypatch.setenv("PL_HOST_CHUNKS", str(req))
+        C = L.pl_host_chunk_rows(m, n, ctypes.cast(buf, ctypes.c_void_p), 64)
+        rows = [int(buf[c]) for c in range(C)]
+        assert 1 <= C <= 64 and sum(rows) == m, (m, n, req, rows)
+        assert all(r >= n for r in rows), (m, n, req, rows)
+        if C > 1:
+            assert len(set(rows[:-1])) == 1 and rows[0] % 128 == 0 and min(rows) >= 4 * n, (m, n, req, rows)
+        if req is not None:
+            assert C <= max(req, 1)
+    monkeypatch.delenv("PL_HOST_CHUNKS", raising=False)
+    assert L.pl_host_chunk_rows(8_000_000, 512, ctypes.cast(buf, ctypes.c_void_p), 64) == 16      # ~2 GiB per chunk
+    assert L.pl_host_chunk_rows(3, 5, ctypes.cast(buf, ctypes.c_void_p), 64) < 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     import pyloworder_b200 as pl

@@ -447,6 +447,26 @@ def RMSE(A_list, B_list, relative: bool = True):
 # --------------------------------------------------------------------------------------
 # sign-/rotation-invariant comparators used by the parity tests
 # --------------------------------------------------------------------------------------
+def energy(A_list, B_list):
+    """Reconstruction energy 1 - sum((A-B)^2)/sum(A^2) over all ranks (pyLOM/vmmath/truncation.py:40-60)."""
+    if isinstance(A_list, np.ndarray):
+        A_list, B_list = [A_list], [B_list]
+    num = sum(np.sum((A - B) ** 2) for A, B in zip(A_list, B_list))
+    den = sum(np.sum(A ** 2) for A in A_list)
+    return 1 - num / den
+
+
+def extract_modes(U, ivar, npoints, modes=(), reshape=True):
+    """pyLOM/POD/utils.py:19-42."""
+    nvars = U.shape[0] // npoints
+    if len(modes) == 0:
+        modes = np.arange(1, U.shape[1] + 1, dtype=np.int32)
+    out = np.zeros((npoints, len(modes)), U.dtype)
+    for i, m in enumerate(modes):
+        out[:, i] = U[ivar - 1:nvars * npoints:nvars, m - 1]
+    return out.reshape((len(modes) * npoints,), order='C') if reshape else out
+
+
 def compare_svd(U_ref, S_ref, V_ref, U, S, V, gap_tol=1e-6, floor=1e-8):
     """Return a dict of parity metrics (SURVEY.md section 8d acceptance).
 

@@ -184,6 +184,23 @@ def test_matmul_vecmat_reconstruct(pl):
     assert np.abs(X - po.reconstruct(U[:, :7], S[:7], V[:7, :])).max() <= 1e-12
 
 
+def test_energy_and_extract_modes(pl):
+    X = synth.snapshots(9000, 20, 4, nvars=3)
+    U, S, V = pl.POD.run(dev(X), remove_mean=False)
+    Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=4)
+    Xr = pl.POD.reconstruct(Ur, Sr, Vr)
+    e = pl.math.energy(dev(X), Xr)
+    assert abs(e - po.energy(X, host(Xr))) <= 1e-13
+    assert abs((1 - e) - po.RMSE(X, host(Xr)) ** 2) <= 1e-13
+    Uh = host(U)
+    for ivar in (1, 2, 3):
+        for modes, reshape in (([], True), ([1, 3, 4], False), ([2], True)):
+            got = pl.POD.extract_modes(U, ivar, 3000, modes=modes, reshape=reshape)
+            ref = po.extract_modes(Uh, ivar, 3000, modes=modes, reshape=reshape)
+            assert np.array_equal(host(got), ref)
+            assert np.array_equal(pl.POD.extract_modes(Uh, ivar, 3000, modes=modes, reshape=reshape), ref)
+
+
 def test_qr_and_svd_entry_points(pl):
     A = synth.random_matrix(3000, 45, 1, cond=1e6)
     Q, R = [host(t) for t in pl.math.qr(dev(A))]

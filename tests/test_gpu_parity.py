@@ -464,6 +464,12 @@ def test_fused_input_read_matches(pl, monkeypatch):
             w.view(torch.float64)[: w.numel() // 8].fill_(float("nan")) if w.numel() % 8 == 0 else w.fill_(255)
         U2, S2, V2 = pl.math.tsqr_svd(A)
         assert torch.equal(S2, S1) and torch.equal(U2, U1)
+        # the memory-saving in-place variant (output buffer = factorisation buffer) with the fused read
+        monkeypatch.setenv("PL_INPLACE", "1")
+        U3, S3, V3 = pl.math.tsqr_svd(A)
+        monkeypatch.delenv("PL_INPLACE")
+        assert torch.equal(A, A0) and torch.equal(S3, S1) and torch.equal(V3, V1)
+        assert float((U3 - U1).abs().max()) <= 1e-14
 
 
 def test_form_q_then_apply_matches(pl):

@@ -15,7 +15,7 @@ from ..utils.cr import cr, cr_start, cr_stop
 from ..utils import parall
 from ..vmmath.averaging import temporal_mean, subtract_mean
 from ..vmmath.maths import matmul, matmul_tn
-from ..vmmath.svd import _tsqr_svd_dev
+from ..vmmath.svd import _tsqr_svd_dev, _engine as _svd_engine
 from ..vmmath.truncation import compute_truncation_residual
 
 
@@ -90,11 +90,20 @@ def run(X, r, remove_mean=True):
         cr_stop('DMD.temporal_mean', 0)
     else:
         Y = Xd
+    muReal, muImag, Phi, bJov = _run_dev(Y, r)
+    dev = Y.device
+    return _out(muReal, kind, dev), _out(muImag, kind, dev), _dev.from_device(Phi, kind), _out(bJov, kind, dev)
+
+
+def _run_dev(Y, r, engine=None):
+    """DMD of the (centred) device matrix Y; `engine` supplies the device operations (tests inject a CPU stand-in to
+    run the multi-rank composition over gloo)."""
+    eng = engine or _svd_engine
     m, n = Y.shape
     if n < 2:
         raise ValueError("DMD.run needs at least two snapshots")
     cr_start('DMD.SVD', 0)
-    U, S, VT, _ = _tsqr_svd_dev(Y[:, :-1].contiguous())
+    U, S, VT, _ = _tsqr_svd_dev(Y[:, :-1].contiguous(), engine=engine)
     cr_stop('DMD.SVD', 0)
     N = int(r) if r >= 1 else compute_truncation_residual(S, r)
     U, S, VT = U[:, :N], S[:N], VT[:N, :]
@@ -102,7 +111,7 @@ def run(X, r, remove_mean=True):
     # Atilde = U^T Y2 V S^-1 with Y2 = Y[:, 1:].  U^T Y is formed over all n columns (16-byte aligned rows) and the
     # first column dropped: one more column of flops instead of the unaligned-load path.
     cr_start('DMD.linear_mapping', 0)
-    aux1 = parall.mpi_reduce(matmul_tn(U, Y), op='sum', all=True)[:, 1:]
+    aux1 = parall.mpi_reduce(eng.matmul_tn(U, Y), op='sum', all=True)[:, 1:]
     S_h, VT_h, aux1_h = _host(S), _host(VT), _host(aux1)
     Atilde = aux1_h @ (VT_h / S_h[:, None]).T
     cr_stop('DMD.linear_mapping', 0)
@@ -112,7 +121,7 @@ def run(X, r, remove_mean=True):
     muReal, muImag = np.real(mu).copy(), np.imag(mu).copy()
     M = ((VT_h.T * (1.0 / S_h)) @ w) / mu                       # (n-1, N): V S^-1 w / mu
     Bm = np.vstack((np.zeros((1, 2 * N)), _interleaved(M)))     # zero row for the dropped first snapshot
-    Phi = torch.view_as_complex(matmul(Y, torch.from_numpy(Bm).to(Y.device)).view(m, N, 2))
+    Phi = torch.view_as_complex(eng.matmul(Y, torch.from_numpy(Bm).to(Y.device)).contiguous().view(m, N, 2))
     cr_stop('DMD.modes', 0)
 
     cr_start('DMD.amplitudes', 0)
@@ -127,8 +136,7 @@ def run(X, r, remove_mean=True):
     cr_start('DMD.order', 0)
     muReal, muImag, Phi, bJov = _order_modes(muReal, muImag, Phi, bJov)
     cr_stop('DMD.order', 0)
-    dev = Y.device
-    return _out(muReal, kind, dev), _out(muImag, kind, dev), _dev.from_device(Phi, kind), _out(bJov, kind, dev)
+    return muReal, muImag, Phi, bJov
 
 
 @cr('DMD.frequency_damping')

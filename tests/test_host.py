@@ -156,6 +156,15 @@ GLOO_SCRIPT = textwrap.dedent("""
     assert np.abs(Sr_.numpy() - So).max() < 1e-12 * So[0]
     ip = parall.mpi_reduce(np.einsum('ik,ik->k', Ul[rank], Ur_.numpy()), op='sum')
     assert np.abs(np.abs(ip) - 1).max() < 1e-8, ip
+    # DMD on the POD basis: SVD of the first n-1 snapshots, projection U^T Y2 (local product + all-reduce), host eig
+    from pyloworder_b200.DMD import wrapper as dmdw
+    Xw = synth.dmd_waves(700, 24, 3)
+    Yw = Xw - Xw.mean(1, keepdims=True)
+    q0, q1 = parall.worksplit(0, 700, rank, size)
+    muR, muI, Phi, bj = dmdw._run_dev(torch.from_numpy(Yw[q0:q1].copy()), 6, engine=CpuEngine())
+    muRo, muIo, Phio, bo = po.dmd_run([Xw[slice(*po.worksplit(0, 700, r, 2))] for r in range(2)], 6)
+    assert np.abs(muR - muRo).max() < 1e-10 and np.abs(muI - muIo).max() < 1e-10
+    assert np.abs(Phi.numpy() * bj - Phio[rank] * bo).max() < 1e-6 * np.abs(bo).max()
     dist.barrier(); dist.destroy_process_group()
     print('RANK_OK_%d' % rank, flush=True)
 """)

@@ -7,7 +7,10 @@
  *   - array arguments are DEVICE pointers unless the name ends in `_host`;
  *   - no hidden malloc on the device: the caller passes a workspace sized by the matching
  *     *_workspace_bytes() query (the reference mallocs/frees scratch inside each call);
- *   - explicit stream (a cudaStream_t passed as void*); calls are stream ordered;
+ *   - explicit stream (a cudaStream_t passed as void*); calls are stream ordered and asynchronous (the Jacobi SVD
+ *     tracks its convergence on the device; only the `_host` entry points and n > 1024 SVDs synchronise);
+ *   - one process may drive several GPUs: internal streams, events and cached buffers are kept per CUDA device, the
+ *     device current at the call must be the one the pointers live on;
  *   - return value 0 = ok, < 0 = bad argument (minus its position), > 0 = CUDA / convergence error;
  *     pl_last_error() returns the message (the reference returns the LAPACK info, svd.pyx:399).
  * Matrices are row-major, contiguous, fp64, exactly as in the reference (C order numpy arrays).
@@ -134,10 +137,37 @@ int pl_host_chunk_rows(int64_t m, int64_t n, int64_t* rows, int max_chunks);
 /* the host entry point keeps its device buffers between calls (grow-only); this releases them */
 void pl_host_cache_free(void);
 
+/* ---- P ranks, ONE collective call per rank (what dtsqr_svd is in the reference: MPI inside, svd.c:565-712) ---------
+ * The communicator wraps an NCCL communicator (libnccl.so.2 is loaded at run time with dlopen; NCCL is only needed
+ * when these entry points are used).  Bootstrap exactly like MPI + NCCL programs do: rank 0 calls
+ * pl_get_unique_id(), the 128 bytes travel to the other ranks by any means (MPI_Bcast in the reference's world, a
+ * file, torch.distributed), every rank calls pl_comm_init_rank() with the CUDA device it drives current.
+ * Replaces MPI_COMM_WORLD + the 2 ceil(log2 P) blocking MPI_Send/MPI_Recv rounds of the butterfly (svd.c:602-669) by
+ * a single ncclAllGather of the n x n R factors. */
+typedef struct pl_comm* pl_comm_t;
+#define PL_UNIQUE_ID_BYTES 128
+int pl_get_unique_id(void* id128);
+int pl_comm_init_rank(pl_comm_t* comm, const void* id128, int rank, int size);
+int pl_comm_rank(pl_comm_t comm);
+int pl_comm_size(pl_comm_t comm);
+int pl_comm_destroy(pl_comm_t comm);
+/* replaces dtsqr_svd (svd.c:678-712) / _drun (POD/wrapper.pyx:95-151) on P ranks, DEVICE pointers: local Householder
+ * QR (R written straight into this rank's slot of the gather buffer), ncclAllGather, QR of the (P n) x n stack and
+ * Jacobi SVD redundantly on every rank (bit-identical S, VT), Ui = Q1_i (Q2_i Ur).  For shards of >= 1 M rows the
+ * explicit Q1 is formed on `stream` while exchange + small factorisations run on an internal high-priority stream.
+ * center != 0: the row means are removed first (X_mean out).  flags bit 0: in-place variant, Ui is the
+ * pl_qr_inplace_rows(m, n) x n buffer.  ws >= pl_tsqr_svd_dist_workspace_bytes(comm, m, n, flags). */
+size_t pl_tsqr_svd_dist_workspace_bytes(pl_comm_t comm, int64_t m, int64_t n, int flags);
+int pl_tsqr_svd_dist_f64(pl_comm_t comm, double* Ui, double* S, double* VT, double* X_mean, const double* Ai, int64_t m,
+                         int64_t n, int center, int flags, void* ws, size_t ws_bytes, void* stream);
+/* the same collective with HOST pointers and the argument list of the reference's dtsqr_svd (+ the communicator):
+ * chunked H2D || factorisation, ncclAllGather of R inside the library, stack SVD, chunked GEMM || D2H. */
+int pl_tsqr_svd_host_dist_f64(pl_comm_t comm, double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n);
+
 /* instrumentation: number of kernel launches issued by this library since load */
 int64_t pl_launch_count(void);
 /* optional CUDA-event timing per kernel class (0 copy/center, 1 panel, 2 update(factor), 3 update(form Q),
- * 4 tall GEMM, 5 small SVD, 6 misc); pl_profile_read synchronises, fills ms / launch counts and resets. */
+ * 4 tall GEMM, 5 small SVD, 6 misc, 7 small-n fused TSQR kernels); pl_profile_read synchronises, fills ms / launch counts and resets. */
 void pl_profile_enable(int on);
 int pl_profile_read(double* ms_by_class, int64_t* launches_by_class, int ncls);
 

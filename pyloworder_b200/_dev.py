@@ -12,8 +12,9 @@ def require_cuda():
         raise RuntimeError("pyloworder_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def to_device(x, what="array"):
@@ -49,15 +50,22 @@ def workspace(nbytes, tag, device):
     """Cached uint8 scratch tensor (torch's caching allocator owns the memory)."""
     key = (tag, device)
     w = _ws_cache.get(key)
-    if w is None or w.numel() < nbytes:
+    if w is None or w.numel() < nbytes + 256:
         _ws_cache.pop(key, None)
+        del w                          # release the old buffer BEFORE allocating the larger one (each is ~ the matrix size)
         w = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
         _ws_cache[key] = w
     off = (-w.data_ptr()) % 256
     return w, w.data_ptr() + off, w.numel() - off
 
 
+def cached_workspace_bytes(tag, device):
+    w = _ws_cache.get((tag, device))
+    return 0 if w is None else w.numel()
+
+
 def free_workspaces():
+    """Release every cached workspace (they are otherwise kept, grow-only, for the next call of the same shape)."""
     _ws_cache.clear()
 
 

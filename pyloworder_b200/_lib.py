@@ -45,6 +45,14 @@ _SIGS = {
     "pl_tsqr_host_factor_f64": (_int, [_vp, _vp, _i64, _i64]),
     "pl_tsqr_host_stack_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     "pl_tsqr_host_apply_f64": (_int, [_vp, _vp, _i64, _i64]),
+    "pl_get_unique_id": (_int, [_vp]),
+    "pl_comm_init_rank": (_int, [ctypes.POINTER(_vp), _vp, _int, _int]),
+    "pl_comm_rank": (_int, [_vp]),
+    "pl_comm_size": (_int, [_vp]),
+    "pl_comm_destroy": (_int, [_vp]),
+    "pl_tsqr_svd_dist_workspace_bytes": (_sz, [_vp, _i64, _i64, _int]),
+    "pl_tsqr_svd_dist_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _sz, _vp]),
+    "pl_tsqr_svd_host_dist_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64]),
     "pl_host_chunk_rows": (_int, [_i64, _i64, _vp, _int]),
     "pl_host_cache_free": (None, []),
     "pl_profile_enable": (None, [_int]),

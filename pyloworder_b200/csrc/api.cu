@@ -303,8 +303,11 @@ static bool svd_overlap_enabled(int64_t m) {
 }
 static int svd_and_apply_overlapped(double* Ui, double* S, double* VT, const double* R, double* Ur, int64_t m, int64_t n,
                                     void* ws, const WsLayout& L, cudaStream_t st, double* Vb_ext) {
-  static cudaStream_t ss = nullptr;
-  static cudaEvent_t eR = nullptr, eS = nullptr;
+  static cudaStream_t ss_d[MAX_DEV] = {};
+  static cudaEvent_t eR_d[MAX_DEV] = {}, eS_d[MAX_DEV] = {};
+  const int dv = cur_dev();
+  cudaStream_t& ss = ss_d[dv];
+  cudaEvent_t &eR = eR_d[dv], &eS = eS_d[dv];
   if (!ss) {
     int lo = 0, hi = 0;
     PL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -344,6 +347,63 @@ static int tsqr_svd_impl(double* Ui, double* S, double* VT, double* X_mean, cons
   if (rc) return rc;
   return qr_apply_q(Ui, n, Ur, n, n, m, n, 0, ws, L, st);
 }
+
+}  // extern "C" (the collective composition below is C++ linkage, called from comm.cu)
+
+// ---- P ranks: local factor -> ncclAllGather of R (in place in the gather buffer) -> stack QR + Jacobi -> apply ----------
+namespace pl {
+struct DistLayout { WsLayout L, Ls; size_t o_rst, o_w, o_stack, total; };
+static DistLayout make_dist_layout(int64_t m, int64_t n, int P, bool inplace) {
+  DistLayout D;
+  D.L = make_layout(m, n, inplace);
+  D.Ls = make_layout((int64_t)P * n, n);
+  size_t off = D.L.total;
+  D.o_rst = off;   off += al((size_t)P * n * n * 8);
+  D.o_w = off;     off += al((size_t)P * n * n * 8);
+  D.o_stack = off; off += D.Ls.total;
+  D.total = off;
+  return D;
+}
+size_t dist_ws_bytes(int64_t m, int64_t n, int P, int flags) {
+  if ((flags & 1) && (n % NB)) return 0;
+  return make_dist_layout(m, n, P, (flags & 1) != 0).total;
+}
+int dist_tsqr_svd(pl_comm* c, double* Ui, double* S, double* VT, double* X_mean, const double* Ai, int64_t m, int64_t n,
+                  int center, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int P = comm_size(c), rank = comm_rank(c);
+  const bool inplace = (flags & 1) != 0;
+  if (inplace && (n % NB)) { set_error("in-place variant needs n %% 32 == 0"); return -10; }
+  DistLayout D = make_dist_layout(m, n, P, inplace);
+  if (!ws || ws_bytes < D.total) { set_error("workspace too small: need %zu bytes, got %zu", D.total, ws_bytes); return -11; }
+  if (reinterpret_cast<uintptr_t>(ws) & 255) { set_error("workspace must be 256-byte aligned"); return -11; }
+  double* Rst = at(ws, D.o_rst);
+  double* Wst = at(ws, D.o_w);
+  void* ws_stack = static_cast<char*>(ws) + D.o_stack;
+  double* Vb_ext = inplace ? Ui : nullptr;
+  // local Householder QR; R_i lands directly in this rank's slot of the gather buffer
+  int rc = qr_factor(Rst + (size_t)rank * n * n, X_mean, Ai, m, n, center, ws, D.L, st, nullptr, Vb_ext);
+  if (rc) return rc;
+  const bool overlap = svd_overlap_enabled(m);
+  cudaStream_t wk = st, side = nullptr;
+  cudaEvent_t eR = nullptr, eS = nullptr;
+  if (overlap) {
+    if ((rc = comm_side(c, &side, &eR, &eS))) return rc;
+    PL_CUDA(cudaEventRecord(eR, st));
+    if ((rc = qr_apply_q(nullptr, n, nullptr, 0, n, m, n, 2, ws, D.L, st, Vb_ext))) return rc;   // explicit Q1 on the main stream
+    PL_CUDA(cudaStreamWaitEvent(side, eR, 0));
+    wk = side;
+  }
+  if ((rc = comm_allgather_inplace(c, Rst, (size_t)n * n, wk))) return rc;
+  if ((rc = tsqr_svd_impl(Wst, S, VT, nullptr, Rst, (int64_t)P * n, n, 0, ws_stack, D.Ls.total, wk))) return rc;   // Wst = Q2 Ur
+  if (overlap) {
+    PL_CUDA(cudaEventRecord(eS, side));
+    PL_CUDA(cudaStreamWaitEvent(st, eS, 0));
+  }
+  return qr_apply_q(Ui, n, Wst + (size_t)rank * n * n, n, n, m, n, overlap ? 1 : 0, ws, D.L, st, Vb_ext);
+}
+}  // namespace pl
+
+extern "C" {
 
 int pl_tsqr_svd_f64(double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n, void* ws, size_t ws_bytes,
                     void* stream) {
@@ -637,6 +697,37 @@ int pl_tsqr_host_stack_f64(double* Wstack, double* S, double* VT, const double* 
   if (!rc && e2 != cudaSuccess) { set_error("CUDA error: %s", cudaGetErrorString(e2)); rc = 1000 + (int)e2; }
   return rc;
 }
+}  // extern "C"
+namespace pl {
+// Host-pointer collective (pl_tsqr_svd_host_dist_f64): the chunked host pipeline around one ncclAllGather.
+int dist_tsqr_svd_host(pl_comm* c, double* Ui, double* S, double* VT, const double* Ai, int64_t m, int64_t n) {
+  const int P = comm_size(c), rank = comm_rank(c);
+  if (P == 1) return pl_tsqr_svd_host_f64(Ui, S, VT, Ai, m, n);
+  int rc = host_factor(Ai, m, n);
+  if (rc) return rc;
+  HostState& H = g_hs;
+  const int64_t m2 = (int64_t)P * n;
+  const WsLayout Ls = make_layout(m2, n);
+  const size_t mat = al((size_t)m2 * n * 8), sq = al((size_t)n * n * 8);
+  char* buf = nullptr;
+  if ((rc = comm_scratch(c, 2 * mat + sq + al((size_t)n * 8) + Ls.total + 256, (void**)&buf))) return rc;
+  buf = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf) + 255) & ~(uintptr_t)255);
+  double* Rst = reinterpret_cast<double*>(buf);
+  double* Wst = reinterpret_cast<double*>(buf + mat);
+  double* dVt = reinterpret_cast<double*>(buf + 2 * mat);
+  double* dS = reinterpret_cast<double*>(buf + 2 * mat + sq);
+  void* ws2 = buf + 2 * mat + sq + al((size_t)n * 8);
+  cudaStream_t s2 = H.s2;
+  PL_CUDA(cudaMemcpyAsync(Rst + (size_t)rank * n * n, at(H.aux, H.o_r2), (size_t)n * n * 8, cudaMemcpyDeviceToDevice, s2));
+  if ((rc = comm_allgather_inplace(c, Rst, (size_t)n * n, s2))) return rc;
+  if ((rc = tsqr_svd_impl(Wst, dS, dVt, nullptr, Rst, m2, n, 0, ws2, Ls.total, s2))) return rc;
+  PL_CUDA(cudaMemcpyAsync(S, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, s2));
+  PL_CUDA(cudaMemcpyAsync(VT, dVt, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s2));
+  return host_apply(Ui, Wst + (size_t)rank * n * n);
+}
+}  // namespace pl
+extern "C" {
+
 int pl_tsqr_host_apply_f64(double* Ui, const double* W, int64_t m, int64_t n) {
   HostState& H = g_hs;
   PL_ARG(H.valid && m == H.m && n == H.n, 3, "apply must follow pl_tsqr_host_factor_f64 with the same m, n");

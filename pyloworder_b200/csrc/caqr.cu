@@ -699,11 +699,9 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   A.C0 = C0; A.ldc0 = ldc0; A.coff0 = coff0; A.nchunk0 = nchunk0;
   A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1;
   A.Csrc = Csrc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_set;
+  if (first_on_device(attr_set))
     PL_CUDA(cudaFuncSetAttribute(caqr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
-    attr_set = true;
-  }
   // strips on grid.y (<= 65535): split very long strip lists over several launches
   int64_t done = 0;
   while (done < L.nstrips) {
@@ -754,8 +752,11 @@ static int launch_panel(const Plan& P, int p, const Level& L, int li, double* Vb
 // two update CTAs fill the register file of an SM (2 x 256 x 128), so a panel CTA only ever replaces an update CTA
 // instead of running beside it.  Off by default; kept for a future update kernel with a smaller footprint.
 int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpiv, cudaStream_t st, const double* Asrc) {
-  static cudaStream_t ss = nullptr;
-  static cudaEvent_t eE = nullptr, eF = nullptr;
+  static cudaStream_t ss_d[MAX_DEV] = {};
+  static cudaEvent_t eE_d[MAX_DEV] = {}, eF_d[MAX_DEV] = {};
+  const int dv = cur_dev();
+  cudaStream_t& ss = ss_d[dv];
+  cudaEvent_t &eE = eE_d[dv], &eF = eF_d[dv];
   const bool look = P.K > 1 && P.panels[0][0].ntiles >= 2048 && getenv("PL_LOOKAHEAD") != nullptr;
   if (look && !ss) {
     int lo = 0, hi = 0;

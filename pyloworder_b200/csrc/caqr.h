@@ -57,3 +57,13 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
 int64_t svd_small_scratch_doubles(int64_t n);
 
 }  // namespace pl
+
+// comm.cu : the NCCL communicator behind the collective entry points
+struct pl_comm;
+namespace pl {
+int comm_allgather_inplace(pl_comm* c, double* buf, size_t count_per_rank, cudaStream_t st);   // rank r's block already at buf + r*count
+int comm_side(pl_comm* c, cudaStream_t* side, cudaEvent_t* eR, cudaEvent_t* eS);
+int comm_rank(const pl_comm* c);
+int comm_size(const pl_comm* c);
+int comm_scratch(pl_comm* c, size_t bytes, void** out);
+}  // namespace pl

@@ -130,11 +130,10 @@ template <int BN>
 static int gemm_tall_launch(double* C, int64_t ldc, const double* A, int64_t lda, const double* Bp, int64_t ldb, int64_t m,
                             int64_t n, int64_t k, cudaStream_t st) {
   const int64_t kp = round_up(k, BK), np = round_up(n, BN);
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (first_on_device(attr)) {
     PL_CUDA(cudaFuncSetAttribute(gemm_tall_kernel<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<BN>)));
     PL_CUDA(cudaFuncSetAttribute(gemm_tall_kernel<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<BN>)));
-    attr = true;
   }
   const bool aligned = ((lda & 1) == 0) && ((k & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   // rows on grid.y (<= 65535 tiles per launch)

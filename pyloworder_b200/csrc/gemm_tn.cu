@@ -167,11 +167,10 @@ static int tn_launch(const TnCfg& c, double* part, const double* X, int64_t ldx,
   const bool aligned = ((ldx & 1) == 0) && ((ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   const size_t smem = sizeof(TnSmem<TA, TB>);
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (first_on_device(attr)) {
     PL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<TA, TB, WA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<TA, TB, WA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   dim3 grid((unsigned)(c.tiles_a * c.tiles_b), (unsigned)c.nsplit);
   if (aligned)

@@ -37,7 +37,7 @@ void count_launches(long long k);   // instrumentation: kernels launched by this
   } while (0)
 
 // ---- optional per-kernel-class event timing (bench.py roofline leg; off by default) ---------
-enum ProfClass { PROF_COPY = 0, PROF_PANEL = 1, PROF_UPDATE_F = 2, PROF_UPDATE_Q = 3, PROF_GEMM = 4, PROF_SVD = 5, PROF_MISC = 6, PROF_NCLS = 7 };
+enum ProfClass { PROF_COPY = 0, PROF_PANEL = 1, PROF_UPDATE_F = 2, PROF_UPDATE_Q = 3, PROF_GEMM = 4, PROF_SVD = 5, PROF_MISC = 6, PROF_SMALL = 7, PROF_NCLS = 8 };
 bool prof_enabled();
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(cudaStream_t st);
@@ -46,6 +46,14 @@ struct ProfScope {
   ProfScope(int cls, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_begin(cls, st); }
   ~ProfScope() { if (on) prof_end(st); }
 };
+
+// ---- per-device state: one process may drive several GPUs (the header's threading note allows it), so streams, events,
+// function attributes and cached device buffers are keyed by the CUDA device that is current at the call.
+constexpr int MAX_DEV = 64;
+static inline int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_DEV) ? d : 0; }
+// One-shot flag per (call site, device): `if (once_per_device(flags)) cudaFuncSetAttribute(...)`.
+struct DevOnce { bool done[MAX_DEV] = {}; };
+static inline bool first_on_device(DevOnce& f) { const int d = cur_dev(); if (f.done[d]) return false; f.done[d] = true; return true; }
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -81,11 +81,31 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
   __syncthreads();
 }
 
+// Convergence state in device memory, so that the host never waits for a sweep (the call stays stream-ordered):
+//   st[0] rotations of the running sweep, st[1] grid-barrier counter (zeroed by a memset before every launch),
+//   st[2] converged flag, st[3] sweeps executed.
+// A fixed budget of sweep launches is enqueued; once a sweep ends without a rotation the remaining launches return
+// at once.  All rotations of a sweep are counted before its last grid barrier, so block 0 sees the final count.
+__device__ __forceinline__ bool sweep_done(const int* st) { return *reinterpret_cast<const volatile int*>(st + 2) != 0; }
+__device__ __forceinline__ void sweep_end(int* st) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (*reinterpret_cast<volatile int*>(st) == 0) st[2] = 1;
+    st[0] = 0;
+    st[3] += 1;
+  }
+}
+// Not converged within the budget: poison S so that the failure is loud wherever the result is read.
+__global__ void jacobi_check_kernel(const int* st, double* S, int n) {
+  if (st[2]) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) S[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
 constexpr int JW = 8;   // warps (row pairs) per CTA
 
 template <int EPL>
 __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
                                                                double tol, int* __restrict__ rotations, unsigned* bar) {
+  if (sweep_done(rotations)) return;                        // converged in an earlier launch of the fixed sweep budget
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * JW + (threadIdx.x >> 5);       // pair index inside a round
   const bool have = i < ne / 2;
@@ -129,6 +149,7 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
     }
     grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
   }
+  sweep_end(rotations);
 }
 
 // Block one-sided Jacobi: a CTA owns a PAIR OF ROW BLOCKS (2*BR rows of G and of J, staged in shared
@@ -140,6 +161,7 @@ template <int BR, int EPL>
 __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
                                                                  double tol, int* __restrict__ rotations, unsigned* bar) {
   extern __shared__ __align__(16) double jsm[];
+  if (sweep_done(rotations)) return;      // converged in an earlier launch of the fixed sweep budget
   double* Gs = jsm;                       // [2*BR][n]
   double* Js = jsm + (size_t)2 * BR * n;  // [2*BR][n]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -225,6 +247,7 @@ __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restr
     }
     grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
   }
+  sweep_end(rotations);
 }
 
 __global__ void __launch_bounds__(128) row_norm_kernel(double* s, const double* Gm, int n, int64_t ld) {
@@ -338,9 +361,11 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   count_launches(2);
   const double tol = 2.0 * std::sqrt((double)n) * 2.220446049250313e-16;
   int sweeps = 0;
+  int* state = rot;                           // {rotations, barrier counter, converged, sweeps executed}
+  unsigned* bar = reinterpret_cast<unsigned*>(rot + 1);
+  bool async_path = false;
   if (ni > 1) {
-    const int max_sweeps = 60;
-    // cooperative single-launch sweeps when all n/2 CTAs can be co-resident
+    // cooperative single-launch sweeps when all CTAs can be co-resident
     int dev = 0, coop = 0, nsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -365,33 +390,42 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
       if (nbe / 2 > nsm) br = 0;
       else PL_CUDA(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     }
-    unsigned* bar = reinterpret_cast<unsigned*>(rot + 1);
-    for (; sweeps < max_sweeps;) {
-      PL_CUDA(cudaMemsetAsync(rot, 0, 2 * sizeof(int), st));
-      if (br) {
-        double tol_ = tol; int ni_ = ni, nbe_ = nbe;
-        void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &rot, &bar};
-        PL_CUDA(cudaLaunchCooperativeKernel(bfn, dim3(nbe / 2), dim3(256), args, bsm, st));
-        count_launches(1);
-      } else if (use_coop) {
-        double tol_ = tol; int ni_ = ni, ne_ = ne;
-        void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &rot, &bar};
-        PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));
-        count_launches(1);
-      } else {
+    PL_CUDA(cudaMemsetAsync(state, 0, 4 * sizeof(int), st));
+    if (br || use_coop) {
+      // Stream-ordered: a fixed budget of sweeps is enqueued, convergence is tracked on the device (no host sync).
+      async_path = true;
+      static const int budget = getenv("PL_JACOBI_SWEEPS") ? atoi(getenv("PL_JACOBI_SWEEPS")) : 40;
+      for (int k = 0; k < budget; k++) {
+        if (k) PL_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        double tol_ = tol; int ni_ = ni, nbe_ = nbe, ne_ = ne;
+        if (br) {
+          void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &state, &bar};
+          PL_CUDA(cudaLaunchCooperativeKernel(bfn, dim3(nbe / 2), dim3(256), args, bsm, st));
+        } else {
+          void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &state, &bar};
+          PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));
+        }
+      }
+      count_launches(budget);
+    } else {
+      // n > 1024 (or no cooperative launch): one launch per round and a host check per sweep.  This rare path
+      // synchronises the stream.
+      const int max_sweeps = 60;
+      for (; sweeps < max_sweeps;) {
+        PL_CUDA(cudaMemsetAsync(state, 0, sizeof(int), st));
         for (int r = 0; r < ne - 1; r++) {
           jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot);
         }
         PL_LAUNCH_CHECK();
         count_launches(ne - 2);
+        int h = 0;
+        PL_CUDA(cudaMemcpyAsync(&h, rot, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PL_CUDA(cudaStreamSynchronize(st));
+        sweeps++;
+        if (h == 0) break;
       }
-      int h = 0;
-      PL_CUDA(cudaMemcpyAsync(&h, rot, sizeof(int), cudaMemcpyDeviceToHost, st));
-      PL_CUDA(cudaStreamSynchronize(st));
-      sweeps++;
-      if (h == 0) break;
+      if (sweeps >= max_sweeps) { set_error("svd_small: Jacobi did not converge in %d sweeps", max_sweeps); return 2; }
     }
-    if (sweeps >= max_sweeps) { set_error("svd_small: Jacobi did not converge in %d sweeps", max_sweeps); return 2; }
   }
   row_norm_kernel<<<ni, 128, 0, st>>>(s, Gm, ni, n);
   rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(rank, s, ni);
@@ -402,8 +436,21 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
     svd_complete_kernel<<<1, 256, 0, st>>>(VT, ldvt, S, ni);
     PL_LAUNCH_CHECK();
   }
-  if (sweeps_out) *sweeps_out = sweeps;
-  if (getenv("PL_DEBUG")) fprintf(stderr, "[pl] svd_small n=%d sweeps=%d\n", ni, sweeps);
+  if (async_path) {
+    jacobi_check_kernel<<<1, 128, 0, st>>>(state, S, ni);
+    PL_LAUNCH_CHECK();
+  }
+  if (sweeps_out || getenv("PL_DEBUG")) {     // debugging only: this synchronises
+    if (async_path) {
+      int h[4] = {0, 0, 0, 0};
+      PL_CUDA(cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+      PL_CUDA(cudaStreamSynchronize(st));
+      sweeps = h[3];
+      if (!h[2]) { set_error("svd_small: Jacobi did not converge in %d sweeps", sweeps); return 2; }
+    }
+    if (sweeps_out) *sweeps_out = sweeps;
+    if (getenv("PL_DEBUG")) fprintf(stderr, "[pl] svd_small n=%d sweeps=%d\n", ni, sweeps);
+  }
   return 0;
 }
 

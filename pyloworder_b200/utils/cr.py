@@ -23,11 +23,18 @@ class _Chan:
         self.tmin = min(self.tmin, dt)
 
 
-def _resolve(ch):
+_MAX_PENDING = 256       # event pairs kept per channel before they are folded into the totals
+
+
+def _resolve(ch, only_done=False):
+    keep = []
     for e0, e1 in ch.pending:
+        if only_done and not e1.query():
+            keep.append((e0, e1))
+            continue
         e1.synchronize()
         ch.add(e0.elapsed_time(e1) * 1e-3)
-    ch.pending = []
+    ch.pending = keep
 
 
 def cr_start(name, suffix=0):
@@ -50,14 +57,32 @@ def cr_stop(name, suffix=0):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         ch.pending.append((s, e))
+        if len(ch.pending) > _MAX_PENDING:      # long runs that never call cr_info(): fold the finished pairs, bounded memory
+            _resolve(ch, only_done=True)
+            if len(ch.pending) > _MAX_PENDING:
+                _resolve(ch)
     else:
         ch.add(time.perf_counter() - s)
 
 
+def _arg_device(args):
+    for x in args:
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.device
+    return None
+
+
 def cr(name):
+    """Channel timer + device guard: the call runs with the CUDA device of its first device-tensor argument current,
+    so streams, workspaces and the library's per-device state all belong to the device the data lives on (a tensor on
+    cuda:1 while cuda:0 is current would otherwise launch on the wrong device)."""
     def deco(fn):
         @functools.wraps(fn)
         def wrap(*a, **k):
+            dev = _arg_device(a)
+            if dev is not None and dev.index != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return wrap(*a, **k)
             cr_start(name)
             try:
                 return fn(*a, **k)

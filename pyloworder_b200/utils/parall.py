@@ -42,6 +42,47 @@ def init_distributed(backend=None):
     return MPI_RANK, MPI_SIZE
 
 
+_c_comm = None
+
+
+def c_comm():
+    """The library's own communicator (pl_comm_t wrapping an NCCL communicator created INSIDE libpylom_b200): rank 0
+    draws the unique id with pl_get_unique_id, the 128 bytes are broadcast over the existing process group, every rank
+    calls pl_comm_init_rank.  This is the handle the collective C entry points (pl_tsqr_svd_dist_f64,
+    pl_tsqr_svd_host_dist_f64) take -- the counterpart of MPI_COMM_WORLD in the reference's dtsqr_svd."""
+    global _c_comm
+    if _c_comm is None:
+        import ctypes
+        from .. import _lib
+        L = _lib.lib()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank() == 0:
+            _lib.check(L.pl_get_unique_id(ident.data_ptr()), "pl_get_unique_id")
+        if is_distributed():
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = ident.to(dev)
+            dist.broadcast(t, 0)
+            ident = t.cpu()
+        h = ctypes.c_void_p()
+        _lib.check(L.pl_comm_init_rank(ctypes.byref(h), ident.data_ptr(), rank(), size()), "pl_comm_init_rank")
+        _c_comm = h
+    return _c_comm
+
+
+def c_comm_destroy():
+    global _c_comm
+    if _c_comm is not None:
+        from .. import _lib
+        _lib.lib().pl_comm_destroy(_c_comm)
+        _c_comm = None
+
+
+def use_c_comm():
+    """The collective C entry point is used whenever the process group runs on NCCL (PL_NO_C_COMM=1 keeps the
+    torch.distributed composition, which is also what the gloo CPU tests exercise)."""
+    return is_distributed() and dist.get_backend() == "nccl" and not os.environ.get("PL_NO_C_COMM")
+
+
 def worksplit(istart, iend, whoAmI, nWorkers=None):
     """Contiguous range of worker `whoAmI`; the remainder goes one each to the lowest ranks
     (pyLOM/utils/parall.py:24-48)."""

@@ -55,6 +55,7 @@ def norm_variance(X, X_mean, X_var):
     return _dev.from_device(out, kind)
 
 
+@cr('math.center')
 def center(X):
     """Fused temporal_mean + subtract_mean: returns (Y, X_mean).  Not in the reference API; it is what
     POD.run does back to back (POD/wrapper.py:33-41)."""

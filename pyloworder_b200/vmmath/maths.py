@@ -58,6 +58,7 @@ def _tall_transposed(A, what):
     return t.T, kind
 
 
+@cr('math.matmul_tn')
 def matmul_tn(X, Y):
     """C(a, b) = X^T Y for two row-major tall device operands X (m, a), Y (m, b): the rank-local part of matmulp
     (transposed-tall DMMA GEMM, reduction over the rows)."""

@@ -43,6 +43,7 @@ def _inplace_ok(m, n, device):
     need = _lib.lib().pl_qr_workspace_bytes(m, n) + m * n * 8
     free, _ = torch.cuda.mem_get_info(device)
     free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    free += _dev.cached_workspace_bytes("local", device)      # an already cached workspace is reused, not allocated again
     return need > 0.92 * free
 
 
@@ -142,6 +143,24 @@ class CudaEngine:
                                     int(center), wp, wb, _dev.stream()), "tsqr_svd")
         return U, S, VT, mean
 
+    def tsqr_svd_dist(self, A, center=False):
+        """P ranks, ONE collective C call (pl_tsqr_svd_dist_f64): local QR, ncclAllGather of R inside the library,
+        redundant stack QR + Jacobi, back-multiply -- the counterpart of the reference's collective dtsqr_svd."""
+        m, n = A.shape
+        L = _lib.lib()
+        comm = parall.c_comm()
+        S = torch.empty(n, dtype=torch.float64, device=A.device)
+        VT = torch.empty((n, n), dtype=torch.float64, device=A.device)
+        mean = torch.empty(m, dtype=torch.float64, device=A.device) if center else None
+        inplace = _inplace_ok(m, n, A.device)
+        flags = 1 if inplace else 0
+        _, wp, wb = _dev.workspace(L.pl_tsqr_svd_dist_workspace_bytes(comm, m, n, flags), "local", A.device)
+        rows = L.pl_qr_inplace_rows(m, n) if inplace else m
+        U = torch.empty((rows, n), dtype=torch.float64, device=A.device)
+        _lib.check(L.pl_tsqr_svd_dist_f64(comm, U.data_ptr(), S.data_ptr(), VT.data_ptr(), _dev.ptr(mean), A.data_ptr(), m, n,
+                                          int(center), flags, wp, wb, _dev.stream()), "tsqr_svd_dist")
+        return U[:m], S, VT, mean
+
     def allgather_rows(self, R):
         return parall.mpi_allgather_rows(R)
 
@@ -160,23 +179,30 @@ class CudaEngine:
 _engine = CudaEngine()
 
 
-def _check_shape(A):
+def _check_shape(A, collective=False):
+    """Shape precondition of the TSQR path.  With `collective` the verdict is all-reduced first, so that every rank
+    raises together instead of one rank raising while the others wait in the exchange."""
     if A.dim() != 2:
         raise ValueError("expected a 2-D array (m, n)")
     m, n = A.shape
-    if m < n:
-        raise ValueError(f"every rank needs at least n rows (got m_i={m} < n={n}); "
+    bad = m < n
+    if collective and parall.is_distributed():
+        bad = bool(parall.mpi_reduce(1.0 if bad else 0.0, op="max") > 0)
+    if bad:
+        raise ValueError(f"every rank needs at least n rows (this rank: m_i={m}, n={n}); "
                          "the reference has the same precondition (pyLOM/vmmath/svd.py:69)")
 
 
 def _tsqr_svd_dev(Ad, center=False, engine=None):
     """Core composition on device tensors.  Returns (U_i, S, VT, mean_i)."""
     eng = engine or _engine
-    _check_shape(Ad)
+    _check_shape(Ad, collective=True)
     P, rank = parall.size(), parall.rank()
     if P == 1:
         return eng.tsqr_svd_single(Ad, center)
     m, n = Ad.shape
+    if engine is None and parall.use_c_comm():
+        return eng.tsqr_svd_dist(Ad, center)
     R_i, mean = eng.factor(Ad, "local", center)
 
     def small_part():
@@ -355,7 +381,9 @@ def update_qr_streaming(Ai, Q1, B1, Yo, r, q):
     B1d, _ = _dev.to_device(B1, "B1")
     Yod, _ = _dev.to_device(Yo, "Yo")
     m, n = Ad.shape
-    r = _check_sketch_shape(m, n, r)
+    r = int(r)
+    if m < r:       # the reference has no r <= n2 restriction here: omega is (n2, r), Yn is (m, r) (svd.py:202-226)
+        raise ValueError(f"every rank needs at least r rows (got m_i={m} < r={r})")
     if _stream_rng is None:
         _stream_rng = _np.random.RandomState()
     Yn = _power_sketch(Ad, _sketch_matrix(n, r, _stream_rng, Ad.device), q, eng)

@@ -194,3 +194,27 @@ def test_dmd_against_reference_golden(path):
         muR, muI, Phi, b = po.dmd_run(bl, r)
         dmd_invariants(g, muR, muI, np.vstack(Phi), b, key)          # the reference's own P-rank run
         dmd_invariants(g, muR, muI, np.vstack(Phi), b, "P1")
+
+
+def test_ref_ranks_processes_match_simulated_butterfly():
+    """oracle/ref_ranks.py runs the reference's P-rank tsqr_svd as P real processes (the bench's CPU arm);
+    its numpy-kernel variant must reproduce the level-synchronous simulation bit for bit in S, and its
+    reference-C-kernel variant (oracle/_ref) to rounding."""
+    import ref_ranks
+    m, n = 3000, 24
+    X = synth.snapshots(m, n, 2022)
+    for P in (2, 3):
+        shards = [X[slice(*po.worksplit(0, m, k, P))] for k in range(P)]
+        Uo, So, Vo = po.tsqr_svd(shards)
+        r = ref_ranks.run(P, m, n, 2022, steps=1, warmup=0, keep=True, use_ref=False)
+        assert all(np.array_equal(r["S"][0], s) for s in r["S"])          # identical on all ranks
+        assert np.array_equal(r["S"][0], So)
+        mt = po.compare_svd(np.vstack(Uo), So, Vo, np.vstack(r["U"]), r["S"][0], r["VT"][0])
+        assert mt["mode_min"] >= 1 - 1e-12
+    if os.path.exists(ref_ranks.REF_SO):
+        r = ref_ranks.run(2, m, n, 2022, steps=1, warmup=0, keep=True, use_ref=True)
+        assert r["kind"] == "reference"
+        shards = [X[slice(*po.worksplit(0, m, k, 2))] for k in range(2)]
+        Uo, So, Vo = po.tsqr_svd(shards)
+        mt = po.compare_svd(np.vstack(Uo), So, Vo, np.vstack(r["U"]), r["S"][0], r["VT"][0])
+        assert mt["sigma_rel"] <= 1e-13 and mt["mode_min"] >= 1 - 1e-10

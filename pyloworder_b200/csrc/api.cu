@@ -3,6 +3,7 @@
 #include "caqr.h"
 #include "../../include/pylom_b200.h"
 #include <atomic>
+#include <memory>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -32,10 +33,40 @@ struct WsLayout {
   Plan plan;
   size_t vb, tws, vup, vpiv, r, bp, ur, svd, vt, s, tmp, total;
   bool ext_vb; int64_t tmp_rows;
+  // small-n path (tsqr_small.cu): reflector store (vb, ld NP), per-tile / per-head T, stacked strip triangles, the
+  // block that seeds pass 2, and the generic layout of the (ns NP) x n stack
+  bool small = false;
+  SmallPlan sp;
+  size_t s_tst = 0, s_thst = 0, s_rst = 0, s_bst = 0, s_inner = 0;
+  std::shared_ptr<WsLayout> inner;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-static WsLayout make_layout(int64_t m, int64_t n, bool ext_vb = false) {
+static WsLayout make_layout(int64_t m, int64_t n, bool ext_vb = false, bool allow_small = true) {
   WsLayout L;
+  if (allow_small && small_eligible(m, n)) {
+    L.small = true;
+    L.sp = small_plan(m, n);
+    const SmallPlan& S = L.sp;
+    L.plan.m = m; L.plan.n = n; L.plan.npad = S.NP; L.plan.K = 0; L.plan.mrows = m;
+    L.plan.t_tiles = L.plan.vup_tiles = L.plan.vpiv_strips = 0;
+    L.ext_vb = ext_vb; L.tmp = 0; L.tmp_rows = 0; L.tws = L.vup = L.vpiv = 0;
+    size_t off = 0;
+    L.vb = off;     if (!ext_vb) off += al((size_t)m * S.NP * 8);
+    L.s_tst = off;  off += al((size_t)S.ntiles * S.tsz * 8);
+    L.s_thst = off; off += al((size_t)S.ns * S.NP * S.NP * 8);
+    L.s_rst = off;  off += al((size_t)S.ns * S.NP * n * 8);
+    L.s_bst = off;  off += al((size_t)S.ns * S.NP * n * 8);
+    L.r = off;      off += al((size_t)n * n * 8);
+    L.bp = off;
+    L.ur = off;     off += al((size_t)n * n * 8);
+    L.vt = off;     off += al((size_t)n * n * 8);
+    L.s = off;      off += al((size_t)n * 8);
+    L.svd = off;    off += al((size_t)svd_small_scratch_doubles(n) * 8);
+    L.inner = std::make_shared<WsLayout>(make_layout(S.ns * S.NP, n, false, false));
+    L.s_inner = off; off += L.inner->total;
+    L.total = off;
+    return L;
+  }
   L.plan = make_plan(m, n);
   const Plan& P = L.plan;
   size_t off = 0;
@@ -72,6 +103,18 @@ static int qr_factor(double* R, double* X_mean, const double* A, int64_t m, int6
   const Plan& P = L.plan;
   double* Vb = Vb_ext ? Vb_ext : at(ws, L.vb);
   int rc;
+  if (L.small) {   // n <= 64: fused tile TSQR (pass 1) -> stacked strip triangles -> generic CAQR of the small stack
+    const SmallPlan& S = L.sp;
+    const double* src = A; int64_t lda = n; int cen = center == 1;
+    if (center == 2) {   // variance normalisation: materialise (A - mean) / var in the reflector store, factor it in place
+      ProfScope ps(PROF_COPY, st);
+      if ((rc = center_var_rows(Vb, S.NP, X_mean, X_var, A, m, n, S.NP, st))) return rc;
+      src = Vb; lda = S.NP; cen = 0;
+    }
+    double* Rst = at(ws, L.s_rst);
+    if ((rc = small_factor(S, src, lda, Vb, S.NP, at(ws, L.s_tst), at(ws, L.s_thst), Rst, n, X_mean, cen, st))) return rc;
+    return qr_factor(R, nullptr, Rst, S.ns * S.NP, n, 0, static_cast<char*>(ws) + L.s_inner, *L.inner, st);
+  }
   // No centering, n a multiple of the panel width, whole row blocks: the first panel's kernels read A directly and the
   // copy pass (8 + 8 bytes per entry) disappears.  PL_NO_FUSED_INPUT / PL_LOOKAHEAD keep the copy.
   const bool fused = !center && P.npad == n && (m % NB) == 0 && P.K > 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
@@ -96,6 +139,15 @@ static int qr_apply_q(double* U, int64_t ldu, const double* W, int64_t ldw, int6
   const Plan& P = L.plan;
   double* Vb = Vb_ext ? Vb_ext : at(ws, L.vb);
   int rc;
+  if (L.small) {   // pass 2 seeded with Q_stack W (explicit Q_stack when W == NULL)
+    const SmallPlan& S = L.sp;
+    if (!W && nw != n) { set_error("apply_q: W == NULL needs nw == n"); return -5; }
+    if (nw > n) { set_error("apply_q: nw > n"); return -5; }
+    double* Bst = at(ws, L.s_bst);
+    if ((rc = qr_apply_q(Bst, nw, W, ldw, nw, S.ns * S.NP, n, flags, static_cast<char*>(ws) + L.s_inner, *L.inner, st))) return rc;
+    if (flags & 2) return 0;
+    return small_apply(S, Vb, S.NP, at(ws, L.s_tst), at(ws, L.s_thst), Bst, nw, U, ldu, (int)nw, st);
+  }
   if (!(flags & 1)) {
     rc = caqr_form_q(P, Vb, at(ws, L.tws), at(ws, L.vup), at(ws, L.vpiv), st);
     if (rc) return rc;
@@ -277,7 +329,7 @@ int pl_pod_run_inplace_f64(double* Ubuf, double* S, double* VT, double* X_mean, 
   rc = qr_factor(R, X_mean, X, m, n, remove_mean ? 1 : 0, ws, L, st, nullptr, Ubuf);
   if (rc) return rc;
   double* Ur = at(ws, L.ur);
-  if (svd_overlap_enabled(m)) return svd_and_apply_overlapped(Ubuf, S, VT, R, Ur, m, n, ws, L, st, Ubuf);
+  if (!L.small && svd_overlap_enabled(m)) return svd_and_apply_overlapped(Ubuf, S, VT, R, Ur, m, n, ws, L, st, Ubuf);
   {
     ProfScope ps(PROF_SVD, st);
     rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
@@ -336,16 +388,18 @@ static int tsqr_svd_impl(double* Ui, double* S, double* VT, double* X_mean, cons
   int rc = check_ws(L, ws, ws_bytes, 9);
   if (rc) return rc;
   double* R = at(ws, L.r);
-  rc = qr_factor(R, X_mean, Ai, m, n, center, ws, L, st);
+  // small-n path with n == NP: the reflectors are written straight into the output (no A-sized buffer at all)
+  double* vext = (L.small && n == L.sp.NP) ? Ui : nullptr;
+  rc = qr_factor(R, X_mean, Ai, m, n, center, ws, L, st, nullptr, vext);
   if (rc) return rc;
   double* Ur = at(ws, L.ur);
-  if (svd_overlap_enabled(m)) return svd_and_apply_overlapped(Ui, S, VT, R, Ur, m, n, ws, L, st, nullptr);
+  if (!L.small && svd_overlap_enabled(m)) return svd_and_apply_overlapped(Ui, S, VT, R, Ur, m, n, ws, L, st, nullptr);
   {
     ProfScope ps(PROF_SVD, st);
     rc = svd_small(Ur, n, S, VT, n, R, n, n, at(ws, L.svd), nullptr, st);
   }
   if (rc) return rc;
-  return qr_apply_q(Ui, n, Ur, n, n, m, n, 0, ws, L, st);
+  return qr_apply_q(Ui, n, Ur, n, n, m, n, 0, ws, L, st, vext);
 }
 
 }  // extern "C" (the collective composition below is C++ linkage, called from comm.cu)
@@ -379,7 +433,7 @@ int dist_tsqr_svd(pl_comm* c, double* Ui, double* S, double* VT, double* X_mean,
   double* Rst = at(ws, D.o_rst);
   double* Wst = at(ws, D.o_w);
   void* ws_stack = static_cast<char*>(ws) + D.o_stack;
-  double* Vb_ext = inplace ? Ui : nullptr;
+  double* Vb_ext = (inplace || (D.L.small && n == D.L.sp.NP)) ? Ui : nullptr;   // small-n path: reflectors go straight into Ui
   // local Householder QR; R_i lands directly in this rank's slot of the gather buffer
   int rc = qr_factor(Rst + (size_t)rank * n * n, X_mean, Ai, m, n, center, ws, D.L, st, nullptr, Vb_ext);
   if (rc) return rc;

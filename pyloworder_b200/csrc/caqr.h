@@ -31,6 +31,27 @@ int caqr_factor(const Plan& P, double* Vb, double* Tws, double* Vup, double* Vpi
 int caqr_extract_r(const Plan& P, const double* Vb, double* R, int64_t ldr, cudaStream_t st);
 int caqr_form_q(const Plan& P, double* Vb, const double* Tws, const double* Vup, const double* Vpiv, cudaStream_t st);
 
+// tsqr_small.cu : fused two-pass TSQR for n <= 64 (strips of a dense NP-row head + 512-row tall tiles, NP = 32 / 64)
+constexpr int STB = 128;   // rows per warp in pass 1 / per slab in pass 2
+constexpr int SRT = 512;   // tall tile rows
+struct SmallPlan {
+  int64_t m; int n, NP;
+  int64_t ns;              // strips
+  int64_t Tt, q, rem;      // whole tiles in total, per strip, strips with one more
+  int64_t ntiles;          // Tt + (part != 0)
+  int part;                // rows of the partial tile at the end of the last strip (0: none; < SRT)
+  int tsz;                 // doubles of T per tile (1024 / 3072)
+};
+SmallPlan small_plan(int64_t m, int64_t n);
+bool small_eligible(int64_t m, int64_t n);
+// pass 1: A (lda, n columns, optional row centering -> mean) -> reflectors V (ldv >= NP; may alias the later output),
+// per-tile T (ntiles * tsz), per-strip head T (ns * NP * NP), stacked strip triangles Rstack ((ns NP) x n, ldr)
+int small_factor(const SmallPlan& P, const double* A, int64_t lda, double* V, int64_t ldv, double* Tst, double* Thst,
+                 double* Rstack, int64_t ldr, double* mean, int center, cudaStream_t st);
+// pass 2: U (m x nw, ldu) = Q [B_s; 0], B ((ns NP) x nw, ldb; destroyed).  U may alias V.
+int small_apply(const SmallPlan& P, const double* V, int64_t ldv, const double* Tst, const double* Thst, double* B, int64_t ldb,
+                double* U, int64_t ldu, int nw, cudaStream_t st);
+
 // center.cu
 int temporal_mean(double* out, const double* X, int64_t m, int64_t n, cudaStream_t st);
 int subtract_mean(double* out, int64_t ldo, const double* X, const double* mean, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st);

@@ -38,7 +38,7 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
 
 // One round of the round-robin ordering: CTA i rotates row pair (p, q).
 __global__ void __launch_bounds__(128) jacobi_round_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
-                                                           int round, double tol, int* __restrict__ rotations) {
+                                                           int round, double tol, int* __restrict__ rotations, const double* __restrict__ fl) {
   __shared__ double sh[3][4];
   const int i = blockIdx.x;
   int p, q;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) jacobi_round_kernel(double* __restrict__ 
   double a = 0, b = 0, c = 0;
   for (int j = threadIdx.x; j < n; j += 128) { double x = gp[j], y = gq[j]; a += x * x; b += y * y; c += x * y; }
   block_sum3(a, b, c, sh);
-  if (c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b)) return;
+  if (c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b) || fmin(a, b) <= fl[0]) return;
   if (threadIdx.x == 0) atomicAdd(rotations, 1);
   const double zeta = (b - a) / (2.0 * c);
   const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -104,8 +104,9 @@ constexpr int JW = 8;   // warps (row pairs) per CTA
 
 template <int EPL>
 __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
-                                                               double tol, int* __restrict__ rotations, unsigned* bar) {
+                                                               double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
   if (sweep_done(rotations)) return;                        // converged in an earlier launch of the fixed sweep budget
+  const double floor2 = fl[0];
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * JW + (threadIdx.x >> 5);       // pair index inside a round
   const bool have = i < ne / 2;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
 #pragma unroll
       for (int e = 0; e < EPL; e++) { a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); c = fma(x[e], y[e], c); }
       a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-      if (!(c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b))) {
+      if (!(c == 0.0 || fabs(c) <= tol * sqrt(a) * sqrt(b) || fmin(a, b) <= floor2)) {
         if (lane == 0) atomicAdd(rotations, 1);
         const double zeta = (b - a) / (2.0 * c);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -159,9 +160,10 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
 // pairs inside a block exactly once per sweep), later rounds rotate only the BR*BR cross pairs.
 template <int BR, int EPL>
 __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
-                                                                 double tol, int* __restrict__ rotations, unsigned* bar) {
+                                                                 double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
   extern __shared__ __align__(16) double jsm[];
   if (sweep_done(rotations)) return;      // converged in an earlier launch of the fixed sweep budget
+  const double floor2 = fl[0];
   double* Gs = jsm;                       // [2*BR][n]
   double* Js = jsm + (size_t)2 * BR * n;  // [2*BR][n]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restr
 #pragma unroll
         for (int e = 0; e < EPL; e++) { sa = fma(xv[e], xv[e], sa); sb = fma(yv[e], yv[e], sb); sc = fma(xv[e], yv[e], sc); }
         sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc);
-        if (!(sc == 0.0 || fabs(sc) <= tol * sqrt(sa) * sqrt(sb))) {
+        if (!(sc == 0.0 || fabs(sc) <= tol * sqrt(sa) * sqrt(sb) || fmin(sa, sb) <= floor2)) {
           if (lane == 0) atomicAdd(rotations, 1);
           const double zeta = (sb - sa) / (2.0 * sc);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -260,6 +262,20 @@ __global__ void __launch_bounds__(128) row_norm_kernel(double* s, const double* 
   if (threadIdx.x == 0) s[blockIdx.x] = sqrt(a);
 }
 
+// Noise floor of the singular values: rows of G whose norm falls below n eps max_k |row_k| are numerically zero (two such
+// rows are never orthogonal RELATIVE to their own norms, so the relative criterion alone would rotate them forever --
+// e.g. an all-zero snapshot column plus a duplicated one).  fl[0] = floor^2 (pairs with a row below it count as converged),
+// fl[1] = floor (rows of V^T below it get an orthonormal completion, like exactly zero ones).
+__global__ void __launch_bounds__(256) jacobi_floor_kernel(double* fl, const double* s, int n) {
+  __shared__ double sh[256];
+  double mx = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) mx = fmax(mx, s[k]);
+  sh[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
+  if (threadIdx.x == 0) { const double f = (double)n * 2.220446049250313e-16 * sh[0]; fl[1] = f; fl[0] = f * f; }
+}
+
 __global__ void rank_kernel(int* rank, const double* s, int n) {
   for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < n; k += blockDim.x * gridDim.x) {
     const double sk = s[k];
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(128) svd_scatter_kernel(double* Ur, int64_t ld
 // Exactly zero singular values (zero rows of G, e.g. an all-zero snapshot column): LAPACK returns an arbitrary
 // orthonormal completion of V^T; do the same.  One CTA; for every zero row try the unit vectors e_0, e_1, ...,
 // orthogonalise twice against all rows already in place and keep the first candidate that survives.
-__global__ void __launch_bounds__(256) svd_complete_kernel(double* VT, int64_t ldvt, const double* S, int n) {
+__global__ void __launch_bounds__(256) svd_complete_kernel(double* VT, int64_t ldvt, const double* S, int n, const double* __restrict__ fl) {
   __shared__ double sh[8];
   __shared__ double s_dot;
   __shared__ int s_ok;
@@ -308,7 +324,7 @@ __global__ void __launch_bounds__(256) svd_complete_kernel(double* VT, int64_t l
   };
   int cand = 0;
   for (int z = 0; z < n; z++) {
-    if (S[z] != 0.0) continue;           // rows are sorted: zeros are at the end, earlier rows are complete
+    if (S[z] > fl[1]) continue;          // rows are sorted: the (numerically) zero ones are at the end, earlier rows are complete
     double* vz = VT + (int64_t)z * ldvt;
     for (; cand < n; cand++) {
       for (int j = tid; j < n; j += 256) vz[j] = (j == cand) ? 1.0 : 0.0;
@@ -350,11 +366,10 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   int* rank = reinterpret_cast<int*>(s + n);
   int* rot = rank + n;     // inside the 64-double tail
   const int ni = (int)n, ne = ni + (ni & 1);
-  if (getenv("PL_JACOBI_NOSORT")) {
-    PL_CUDA(cudaMemsetAsync(s, 0, (size_t)n * 8, st));     // equal keys -> rank = identity
-  } else {
-    row_norm_kernel<<<ni, 128, 0, st>>>(s, R, ni, ldr);
-  }
+  double* fl = scratch + 2 * n * n + 2 * n + 56;   // {floor^2, floor}: inside the 64-double tail, behind rank / state
+  row_norm_kernel<<<ni, 128, 0, st>>>(s, R, ni, ldr);
+  jacobi_floor_kernel<<<1, 256, 0, st>>>(fl, s, ni);
+  if (getenv("PL_JACOBI_NOSORT")) PL_CUDA(cudaMemsetAsync(s, 0, (size_t)n * 8, st));     // equal keys -> rank = identity
   rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(rank, s, ni);
   jacobi_init_kernel<<<(unsigned)ceil_div(n * n, 256), 256, 0, st>>>(Gm, J, R, ldr, ni, rank);
   PL_LAUNCH_CHECK();
@@ -399,10 +414,10 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
         if (k) PL_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
         double tol_ = tol; int ni_ = ni, nbe_ = nbe, ne_ = ne;
         if (br) {
-          void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &state, &bar};
+          void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &state, &bar, &fl};
           PL_CUDA(cudaLaunchCooperativeKernel(bfn, dim3(nbe / 2), dim3(256), args, bsm, st));
         } else {
-          void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &state, &bar};
+          void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &state, &bar, &fl};
           PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));
         }
       }
@@ -414,7 +429,7 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
       for (; sweeps < max_sweeps;) {
         PL_CUDA(cudaMemsetAsync(state, 0, sizeof(int), st));
         for (int r = 0; r < ne - 1; r++) {
-          jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot);
+          jacobi_round_kernel<<<ne / 2, 128, 0, st>>>(Gm, J, ni, ne, r, tol, rot, fl);
         }
         PL_LAUNCH_CHECK();
         count_launches(ne - 2);
@@ -432,8 +447,8 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   svd_scatter_kernel<<<ni, 128, 0, st>>>(Ur, ldu, S, VT, ldvt, Gm, J, s, rank, ni);
   PL_LAUNCH_CHECK();
   count_launches(2);
-  if (ldvt == n || true) {   // fill the rows of V^T that belong to exactly zero singular values
-    svd_complete_kernel<<<1, 256, 0, st>>>(VT, ldvt, S, ni);
+  {   // fill the rows of V^T that belong to exactly zero singular values
+    svd_complete_kernel<<<1, 256, 0, st>>>(VT, ldvt, S, ni, fl);
     PL_LAUNCH_CHECK();
   }
   if (async_path) {

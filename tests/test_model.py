@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 import model_caqr as mc
+import model_tsqr_small as ms
 import synth
 
 
@@ -54,3 +55,27 @@ def test_jacobi_model(n, cond):
     assert np.abs(Vt @ Vt.T - np.eye(n)).max() < 1e-12
     assert np.abs((Ur * S) @ Vt - R).max() <= 1e-13 * Sref[0]
     assert sweeps < 20
+
+
+@pytest.mark.parametrize("m,n,NP,kind", [(9000, 64, 64, "rand"), (12000, 50, 64, "center"), (7000, 32, 32, "rand"),
+                                         (9000, 20, 32, "cond"), (5300, 64, 64, "rand"), (20000, 64, 64, "def")])
+def test_tsqr_small_model(m, n, NP, kind):
+    """The two-pass tile TSQR of csrc/tsqr_small.cu (dense head + left-looking structured tiles with an accumulated
+    T, zero-block back-multiply) against LAPACK: several strips, a partial last tile, rank-deficient input."""
+    rng = np.random.default_rng(m + n)
+    if kind == "center":
+        A = synth.snapshots(m, n, 3); A = A - A.mean(axis=1, keepdims=True)
+    elif kind == "cond":
+        A = synth.random_matrix(m, n, 2, cond=1e12)
+    else:
+        A = rng.standard_normal((m, n))
+        if kind == "def":
+            A[:, 5] = 0.0; A[:, 17] = A[:, 3]
+    Q, R = ms.qr(A, NP, nstrips_target=5, min_tiles=2)
+    sc = np.abs(A).max()
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 5e-14
+    assert np.abs(Q @ R - A).max() <= 1e-13 * sc * n
+    # strips: NP head rows + whole 512-row tiles, only the last strip may end with a partial tile
+    strips = ms.plan(m, NP, 5, 2)
+    assert sum(NP + (nt - 1) * ms.TB + last for _, nt, last in strips) == m
+    assert all(last == ms.TB for _, _, last in strips[:-1])

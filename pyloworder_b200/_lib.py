@@ -6,7 +6,8 @@ entry point raises.  PyTorch is used for device buffers, streams and torch.distr
 import ctypes, os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libpylom_b200.so")
+# PL_LIBPATH: an instrumented build of the same sources (probes/build_variant.sh); still the CUDA library, never a CPU path
+_LIBPATH = os.environ.get("PL_LIBPATH") or os.path.join(_HERE, "libpylom_b200.so")
 _lib = None
 
 _i64, _int, _vp, _sz = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t

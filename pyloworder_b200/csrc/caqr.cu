@@ -21,6 +21,7 @@
 #include "caqr.h"
 #include <vector>
 #include <cstdlib>
+#include <type_traits>
 
 namespace pl {
 
@@ -418,7 +419,7 @@ struct UpdArgs {
   int64_t nblk, bs, ntiles; int s; int upper; int forward;
   const double* Tl; const double* Vupl; const double* Vpivl; int virt;
   double* C0; int64_t ldc0; int coff0; int nchunk0;
-  double* C1; int64_t ldc1; int coff1;
+  double* C1; int64_t ldc1; int coff1; int nchunk1;
   const double* Csrc;   // forward pass only: C is READ from here (same ld / offsets), written to C0/C1; nullptr = in place
   int dbg;      // timing experiments only (PL_UPD_DBG): 1 no staging, 2 no GEMM1, 4 no T step, 8 no GEMM2, 16 no stores, 32 GEMM1 fragments once, 64 no L2 prefetch
 };
@@ -656,6 +657,348 @@ __global__ void __launch_bounds__(256, 2) caqr_update_kernel(UpdArgs A) {
 }
 
 // =============================================================================================
+// update kernel, second generation: WARP-PRIVATE COLUMNS
+// =============================================================================================
+// A CTA still walks one strip of tiles for a group of trailing columns, but every WARP owns 8 columns for itself
+// (NW warps = NW * 8 columns per CTA).  The m8n8k4 FP64 MMA is used with the COLUMNS as the M index everywhere:
+//     GEMM1   W^T (8 x 32)  = Z^T + C^T V          A = C block from REGISTERS, B = V from shared memory
+//     T step  W'^T (8 x 32) = W^T op(T)^T          A = W^T from registers,      B = T from shared memory
+//     GEMM2   C^T (8 x rows) -= W'^T V^T           A = W'^T from registers,     B = V from shared memory, D = C block
+// The accumulator layout of one product (lane (g, t) holds D[g][2t], D[g][2t+1]) is a legal A-operand layout of the
+// next one once the K index is permuted accordingly (the B operand is fetched from shared memory with the same
+// permutation), so W, W', the carried block Z and the C blocks never leave the registers, nothing is transposed, and
+// the warps of a CTA share only the staged V and T tiles: ONE block barrier per tile (double-buffered cp.async
+// staging), no lock-step phases.  C goes from global memory straight into the MMA fragments (read once from HBM for
+// GEMM1, once more from L2 for GEMM2, one block ahead of its use) and never through shared memory; every 16-byte
+// shared-memory load feeds two MMAs (the M / K permutations pair adjacent reflectors), which is 44 % of the
+// shared-memory bandwidth at the full DMMA rate.  V and T are stored dense with an XOR swizzle of their 16-byte
+// chunks that makes all three fragment access patterns conflict free.
+//
+// Index conventions (g = lane >> 2, t = lane & 3):
+//   C block (32 rows x 8 columns), cb[rb][e]  = C[row 8 rb + 2 t + e][column g]
+//   reflector-indexed blocks (Z^T, W^T, W'^T), x[a][h] with a = 2 pr + e' = X^T[column g][reflector 16 pr + 4 t + 2 h + e']
+__device__ __forceinline__ void mma884u(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// dense NB-column tiles in shared memory, 16-byte chunk c of row r stored at chunk (c ^ swz(r))
+__device__ __forceinline__ int vswz(int r) { return r & 7; }
+__device__ __forceinline__ int tswz(int r) { return ((r >> 1) & 6) | ((r >> 1) & 1); }
+__device__ __forceinline__ const double2* vchunk(const double* Vt, int r, int c) {
+  return reinterpret_cast<const double2*>(Vt + r * NB + 2 * (c ^ vswz(r)));
+}
+__device__ __forceinline__ const double2* tchunk(const double* Tt, int r, int c) {
+  return reinterpret_cast<const double2*>(Tt + r * NB + 2 * (c ^ tswz(r)));
+}
+
+template <int NW>
+struct Upd2Smem {
+  double V[2][TB * NB];
+  double T[2][NB * NB];
+  double2 Z[NW][4][32];      // carried block of every warp between tiles: Z[warp][a][lane] = (z[a][0], z[a][1])
+};
+
+// explicit loads: the PTX order of these (volatile) statements relative to the MMAs is the software pipeline
+__device__ __forceinline__ double ldg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void lds_v2(double2& v, unsigned addr) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+}
+
+template <int NW, bool fwd, bool VIRT>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) caqr_update2_kernel(UpdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Upd2Smem<NW>& S = *reinterpret_cast<Upd2Smem<NW>*>(smem_raw);
+  constexpr int NT = NW * 32;
+  constexpr int CPW = NB / 8;                       // warps per 32-column chunk
+  const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+  // ---- this warp's 8 columns
+  const int chunk = blockIdx.x * (NW / CPW) + warp / CPW;
+  const bool active = chunk < A.nchunk0 + A.nchunk1;
+  const bool grp0 = chunk < A.nchunk0;
+  double* Cb = grp0 ? A.C0 : A.C1;
+  const int64_t ldc = grp0 ? A.ldc0 : A.ldc1;
+  const int coffw = (grp0 ? A.coff0 + NB * chunk : A.coff1 + NB * (chunk - A.nchunk0)) + 8 * (warp % CPW);
+  constexpr bool virt = VIRT;                      // virtual-zero launches have no second column group
+  const double* Lb = A.Csrc ? A.Csrc : Cb;
+  const bool upper = A.upper != 0;
+
+  const int64_t t0 = (int64_t)blockIdx.y * A.s;
+  int cnt = A.s;
+  if (t0 + cnt > A.ntiles) cnt = (int)(A.ntiles - t0);
+  const int64_t pivrow = A.row0 + t0 * G * A.bs;
+
+  // ---- staging geometry: thread -> 16-byte chunk (row tid / 16 (+ k NT / 16), chunk tid % 16)
+  const int sr = tid >> 4, sc = tid & 15;
+  auto stage = [&](int64_t tt, bool first_tile, int buf) {
+    double* Vs = S.V[buf];
+    double* Ts = S.T[buf];
+#pragma unroll
+    for (int k = 0; k < TB / (NT / 16); k++) {
+      const int r = sr + k * (NT / 16);             // row of the tile
+      const int q = r >> 5, rr = r & 31;
+      const bool valid = (tt * G + q) < A.nblk;
+      const double* src;
+      bool ok = true;
+      if (upper) src = A.Vupl + (tt * TB + r) * NB + 2 * sc;
+      else if (q == 0 && first_tile) src = A.Vpivl + (int64_t)blockIdx.y * (NB * NB) + rr * NB + 2 * sc;
+      else { src = A.Vb + (A.row0 + ((valid ? tt * G + q : 0)) * A.bs + rr) * A.ld + A.col0 + 2 * sc; ok = valid; }
+      cp_async16(Vs + r * NB + 2 * (sc ^ vswz(r)), src, ok);
+    }
+#pragma unroll
+    for (int k = 0; k < NB / (NT / 16); k++) {
+      const int r = sr + k * (NT / 16);
+      cp_async16(Ts + r * NB + 2 * (sc ^ tswz(r)), A.Tl + tt * (NB * NB) + r * NB + 2 * sc, true);
+    }
+  };
+  // ---- C blocks: (warp-uniform block base) + (lane offset) + (8 rb + e) rows.  The whole tile (4 blocks) of this
+  //      warp's columns lives in registers from its load to its store; c[q] is refilled with the NEXT tile's block q
+  //      right after it has been stored, and both GEMMs walk the blocks in the order 3, 2, 1, 0, so that every block has
+  //      most of a tile's time to arrive.
+  const int64_t lane_off = (int64_t)(2 * t) * ldc + g;
+  auto blk_base = [&](const double* base, int64_t tt, int q) -> const double* {     // warp uniform
+    return base + (A.row0 + (tt * G + q) * A.bs) * ldc + coffw;
+  };
+  auto load_blk = [&](double (&cb)[4][2], const double* ub, bool ok) {
+    if (ok) {
+      const double* p = ub + lane_off;
+#pragma unroll
+      for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) cb[rb][e] = ldg_f64(p + (8 * rb + e) * ldc);
+    } else {
+#pragma unroll
+      for (int rb = 0; rb < 4; rb++) { cb[rb][0] = 0.0; cb[rb][1] = 0.0; }
+    }
+  };
+  auto store_blk = [&](const double (&cb)[4][2], double* ub) {
+    double* p = ub + lane_off;
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) p[(8 * rb + e) * ldc] = cb[rb][e];
+  };
+  double c[G][4][2];
+
+  // carried block Z^T: z[a][h] = Z[row 16 pr + 4 t + 2 h + e'][column], a = 2 pr + e'; kept in shared memory between
+  // tiles (the first tile of a strip, whose block 0 is the pivot block, holds it in the registers of c[0])
+  double2* zs = &S.Z[warp][0][lane];               // zs[32 * a]
+  auto z_ptr = [&](const double* base) -> const double* { return base + (pivrow + 4 * t) * ldc + coffw + g; };
+  if (active) {
+    const double* p = z_ptr(fwd ? Lb : Cb);        // forward: the pivot rows of the strip's first tile, read from the source
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      zs[32 * a] = make_double2(p[(int64_t)(16 * (a >> 1) + (a & 1)) * ldc], p[(int64_t)(16 * (a >> 1) + 2 + (a & 1)) * ldc]);
+  }
+
+  // ---- shared-memory fragment addresses (bytes): per-lane parts of the two regular access patterns
+  const unsigned sV0 = (unsigned)__cvta_generic_to_shared(&S.V[0][0]);
+  const unsigned sT0 = (unsigned)__cvta_generic_to_shared(&S.T[0][0]);
+  unsigned o1[2][2], o2[2][2];
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+      o1[e][pr] = (unsigned)((2 * t + e) * 256 + ((8 * pr + g) ^ (2 * t + e)) * 16);   // row 2t+e (+8k), chunk 8pr+g
+      o2[pr][e] = (unsigned)(g * 256 + ((8 * pr + 2 * t + e) ^ g) * 16);               // row g (+8k), chunk 8pr+2t+e
+    }
+  auto voff = [&](int r, int cch) -> unsigned { return (unsigned)(r * 256 + ((cch ^ vswz(r)) * 16)); };
+  auto toff = [&](int r, int cch) -> unsigned { return (unsigned)(r * 256 + ((cch ^ tswz(r)) * 16)); };
+
+  const int i0 = fwd ? 0 : cnt - 1;
+  stage(t0 + i0, i0 == 0, 0);
+  cp_async_commit();
+  if (!virt) {                                     // all C blocks of the first tile
+#pragma unroll
+    for (int qq = 0; qq < G; qq++) {
+      const int q = G - 1 - qq;
+      if (q == 0 && i0 == 0) continue;             // pivot block: its rows are the carried block
+      load_blk(c[q], blk_base(Lb, t0 + i0, q), active && ((t0 + i0) * G + q) < A.nblk);
+    }
+  }
+
+  // one tile; FIRST (the strip's first tile, whose slab 0 is the pivot block) is a compile-time constant
+  auto tile = [&](auto first_c, int it, int i) {
+    constexpr bool first = decltype(first_c)::value;
+    const int64_t tt = t0 + i;
+    const int buf = it & 1;
+    cp_async_wait<0>();
+    __syncthreads();                      // tile `it` has landed for everybody; everybody is done with tile it-1
+    const int in = fwd ? i + 1 : i - 1;   // next tile of the strip (valid when it + 1 < cnt)
+    const bool more = it + 1 < cnt;
+    if (more) stage(t0 + in, in == 0, buf ^ 1);
+    cp_async_commit();
+    if (!active) return;
+    const unsigned sV = sV0 + (unsigned)buf * (TB * NB * 8);
+    const unsigned sT = sT0 + (unsigned)buf * (NB * NB * 8);
+    double (&z)[4][2] = c[0];             // first tile only: the carried block in the registers of the (unused) block 0
+
+    // ---- GEMM1: W^T = Z^T + C^T V   (first tile: slab 0 is the pivot block, whose C rows are the carried block)
+    double w[4][2];
+    if (first) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) { const double2 v = zs[32 * a]; z[a][0] = v.x; z[a][1] = v.y; w[a][0] = 0.0; w[a][1] = 0.0; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int r = 16 * (a >> 1) + 4 * t + 2 * h + (a & 1);
+          double2 b[2];
+          lds_v2(b[0], sV + voff(r, g)); lds_v2(b[1], sV + voff(r, 8 + g));
+#pragma unroll
+          for (int pr = 0; pr < 2; pr++) {
+            mma884u(w[2 * pr], z[a][h], b[pr].x);
+            mma884u(w[2 * pr + 1], z[a][h], b[pr].y);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; a++) { const double2 v = zs[32 * a]; w[a][0] = v.x; w[a][1] = v.y; }
+    }
+    if (!virt) {
+#pragma unroll
+      for (int qq = 0; qq < G; qq++) {
+        const int q = G - 1 - qq;
+        if (first && q == 0) continue;
+        double2 b[2][2];                                   // [k-step parity][pr]: fragments one k-step ahead
+        lds_v2(b[0][0], sV + o1[0][0] + (32 * q) * 256); lds_v2(b[0][1], sV + o1[0][1] + (32 * q) * 256);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          const int rb = ks >> 1, e = ks & 1;
+          if (ks + 1 < 8) {
+            const int rbn = (ks + 1) >> 1, en = (ks + 1) & 1;
+            lds_v2(b[(ks + 1) & 1][0], sV + o1[en][0] + (32 * q + 8 * rbn) * 256);
+            lds_v2(b[(ks + 1) & 1][1], sV + o1[en][1] + (32 * q + 8 * rbn) * 256);
+          }
+#pragma unroll
+          for (int pr = 0; pr < 2; pr++) {
+            mma884u(w[2 * pr], c[q][rb][e], b[ks & 1][pr].x);
+            mma884u(w[2 * pr + 1], c[q][rb][e], b[ks & 1][pr].y);
+          }
+        }
+      }
+    }
+    // ---- T step: W'^T = W^T op(T)^T   (forward: op(T) = T^T, backward: op(T) = T); wp holds -W'^T
+    double wp[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { wp[a][0] = 0.0; wp[a][1] = 0.0; }
+    if (fwd) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int r = 16 * (a >> 1) + 4 * t + 2 * h + (a & 1);
+          double2 b[2];
+          lds_v2(b[0], sT + toff(r, g)); lds_v2(b[1], sT + toff(r, 8 + g));
+#pragma unroll
+          for (int pr = 0; pr < 2; pr++) {
+            mma884u(wp[2 * pr], w[a][h], b[pr].x);
+            mma884u(wp[2 * pr + 1], w[a][h], b[pr].y);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int pr = 0; pr < 2; pr++) {
+        double2 b0[4], b1[4];
+#pragma unroll
+        for (int a2 = 0; a2 < 4; a2++) {
+          const int r = 16 * (a2 >> 1) + 2 * g + (a2 & 1);
+          lds_v2(b0[a2], sT + toff(r, 8 * pr + 2 * t)); lds_v2(b1[a2], sT + toff(r, 8 * pr + 2 * t + 1));
+        }
+#pragma unroll
+        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr][0], b0[a2].x);
+#pragma unroll
+        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr + 1][0], b0[a2].y);
+#pragma unroll
+        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr][1], b1[a2].x);
+#pragma unroll
+        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr + 1][1], b1[a2].y);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      if (!first) { const double2 v = zs[32 * a]; zs[32 * a] = make_double2(v.x - wp[a][0], v.y - wp[a][1]); }   // Z -= W'
+      wp[a][0] = -wp[a][0]; wp[a][1] = -wp[a][1];
+    }
+    // ---- GEMM2: C^T -= W'^T V^T, same block order; a stored block's registers take the next tile's block at once
+#pragma unroll
+    for (int qq = 0; qq < G; qq++) {
+      const int q = G - 1 - qq;
+      if (first && q == 0) {
+        // pivot slab: Z^T -= W'^T V0^T, D[g][2 t + h] <-> row 16 pr + 2 (2 t + h) + e'
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++) {
+          double2 b0[4], b1[4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int r = 16 * (a >> 1) + 2 * g + (a & 1);
+            lds_v2(b0[a], sV + voff(r, 8 * pr + 2 * t)); lds_v2(b1[a], sV + voff(r, 8 * pr + 2 * t + 1));
+          }
+#pragma unroll
+          for (int a = 0; a < 4; a++) mma884u(z[a], wp[2 * pr][0], b0[a].x);
+#pragma unroll
+          for (int a = 0; a < 4; a++) mma884u(z[a], wp[2 * pr + 1][0], b0[a].y);
+#pragma unroll
+          for (int a = 0; a < 4; a++) mma884u(z[a], wp[2 * pr][1], b1[a].x);
+#pragma unroll
+          for (int a = 0; a < 4; a++) mma884u(z[a], wp[2 * pr + 1][1], b1[a].y);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) zs[32 * a] = make_double2(z[a][0], z[a][1]);
+      } else {
+        if (virt) {
+#pragma unroll
+          for (int rb = 0; rb < 4; rb++) { c[q][rb][0] = 0.0; c[q][rb][1] = 0.0; }
+        }
+        // units (pr, j): one 16-byte fragment load per 8-row group feeds two MMAs
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int pr = u >> 1, j = u & 1;
+          double2 b[4];
+#pragma unroll
+          for (int rb = 0; rb < 4; rb++) lds_v2(b[rb], sV + o2[pr][j] + (32 * q + 8 * rb) * 256);
+#pragma unroll
+          for (int rb = 0; rb < 4; rb++) mma884u(c[q][rb], wp[2 * pr][j], b[rb].x);
+#pragma unroll
+          for (int rb = 0; rb < 4; rb++) mma884u(c[q][rb], wp[2 * pr + 1][j], b[rb].y);
+        }
+        if ((tt * G + q) < A.nblk) store_blk(c[q], const_cast<double*>(blk_base(Cb, tt, q)));
+      }
+      if (!virt && more && !(q == 0 && in == 0))     // block q of the next tile (not its pivot block)
+        load_blk(c[q], blk_base(Lb, t0 + in, q), ((t0 + in) * G + q) < A.nblk);
+    }
+    if (more && !virt) {                             // the tile after the next one -> L2 (this warp's 64-byte row pieces)
+      const int i2 = fwd ? i + 2 : i - 2;
+      if (it + 2 < cnt) {
+        const int64_t tn = t0 + i2;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((tn * G + k) < A.nblk)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Lb + (A.row0 + (tn * G + k) * A.bs + lane) * ldc + coffw));
+      }
+    }
+  };
+  for (int it = 0; it < cnt; it++) {
+    const int i = fwd ? it : (cnt - 1 - it);
+    if (i == 0) tile(std::true_type{}, it, i); else tile(std::false_type{}, it, i);
+  }
+  // ---- carried rows back to the pivot block rows
+  if (active) {
+    double* p = const_cast<double*>(z_ptr(Cb));
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double2 v = zs[32 * a];
+      p[(int64_t)(16 * (a >> 1) + (a & 1)) * ldc] = v.x;
+      p[(int64_t)(16 * (a >> 1) + 2 + (a & 1)) * ldc] = v.y;
+    }
+  }
+}
+
+// =============================================================================================
 // small helper kernels
 // =============================================================================================
 // R (n x n, ld n) <- upper triangle of Vb[0:n, 0:n]
@@ -697,11 +1040,22 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
   static const int upd_dbg = getenv("PL_UPD_DBG") ? atoi(getenv("PL_UPD_DBG")) : 0;
   A.dbg = upd_dbg;
   A.C0 = C0; A.ldc0 = ldc0; A.coff0 = coff0; A.nchunk0 = nchunk0;
-  A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1;
+  A.C1 = C1; A.ldc1 = ldc1; A.coff1 = coff1; A.nchunk1 = nchunk1;
   A.Csrc = Csrc;
   static DevOnce attr_set;
-  if (first_on_device(attr_set))
+  if (first_on_device(attr_set)) {
     PL_CUDA(cudaFuncSetAttribute(caqr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
+    const int sm2 = (int)sizeof(Upd2Smem<8>);
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    PL_CUDA(cudaFuncSetAttribute(caqr_update2_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+  }
+  static const bool upd_old = getenv("PL_UPD_OLD") != nullptr;   // first-generation kernel (A/B timing only)
   // strips on grid.y (<= 65535): split very long strip lists over several launches
   int64_t done = 0;
   while (done < L.nstrips) {
@@ -714,10 +1068,25 @@ static int launch_update(const Plan& P, int p, const Level& L, int li, const dou
     B.Tl = A.Tl + done * L.s * (NB * NB);
     if (B.Vupl) B.Vupl = A.Vupl + done * L.s * (TB * NB);
     if (B.Vpivl) B.Vpivl = A.Vpivl + done * (NB * NB);
-    dim3 grid((unsigned)(nchunk0 + nchunk1), (unsigned)ny);
+    const int nch = nchunk0 + nchunk1;
     {
       ProfScope ps(forward ? PROF_UPDATE_F : PROF_UPDATE_Q, st);
-      caqr_update_kernel<<<grid, 256, sizeof(UpdSmem), st>>>(B);
+      if (upd_old) {
+        dim3 grid((unsigned)nch, (unsigned)ny);
+        caqr_update_kernel<<<grid, 256, sizeof(UpdSmem), st>>>(B);
+      } else {
+        const bool one = nch == 1;
+        dim3 grid(one ? 1u : (unsigned)((nch + 1) / 2), (unsigned)ny);
+        const int nt = one ? 128 : 256;
+        const size_t sm = sizeof(Upd2Smem<8>);
+        void (*fn)(UpdArgs) = nullptr;
+        const bool vt = virt != 0 && nchunk0 > 0;
+        if (vt && nchunk1 > 0) { set_error("launch_update: a virtual-zero launch takes one column group"); return -1; }
+#define PL_UPD2(NWv) (forward ? (vt ? caqr_update2_kernel<NWv, true, true> : caqr_update2_kernel<NWv, true, false>) \
+                              : (vt ? caqr_update2_kernel<NWv, false, true> : caqr_update2_kernel<NWv, false, false>))
+        fn = one ? PL_UPD2(4) : PL_UPD2(8);
+        fn<<<grid, nt, sm, st>>>(B);
+      }
     }
     PL_LAUNCH_CHECK();
     done += ny;

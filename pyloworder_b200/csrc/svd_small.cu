@@ -306,51 +306,69 @@ __global__ void __launch_bounds__(128) svd_scatter_kernel(double* Ur, int64_t ld
   }
 }
 
-// Exactly zero singular values (zero rows of G, e.g. an all-zero snapshot column): LAPACK returns an arbitrary
-// orthonormal completion of V^T; do the same.  One CTA; for every zero row try the unit vectors e_0, e_1, ...,
-// orthogonalise twice against all rows already in place and keep the first candidate that survives.
-__global__ void __launch_bounds__(256) svd_complete_kernel(double* VT, int64_t ldvt, const double* S, int n, const double* __restrict__ fl) {
-  __shared__ double sh[8];
-  __shared__ double s_dot;
-  __shared__ int s_ok;
+// Zero (or numerically zero: below the noise floor) singular values, e.g. an all-zero snapshot column or the null
+// direction of centred data: LAPACK returns an orthonormal completion of V^T; do the same.  One CTA; for every such row
+// try the unit vectors e_0, e_1, ..., orthogonalise against all rows already in place (classical Gram-Schmidt, all inner
+// products of a pass computed at once, one warp per row) and keep the first candidate whose remainder is long enough.
+// A remaining null space of dimension >= 1 holds some e_j with squared projection >= 1/n (the squared projections of
+// e_0..e_{n-1} sum to the dimension), so the threshold 1/(2n) always finds one; three passes + a renormalisation in
+// between bring the row to working-precision orthogonality whatever the cancellation of the first pass was.
+__global__ void __launch_bounds__(1024) svd_complete_kernel(double* VT, int64_t ldvt, const double* S, int n, const double* __restrict__ fl) {
+  extern __shared__ double dots[];      // n inner products
+  __shared__ double sh[32];
+  __shared__ double s_nn;
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-  auto bsum = [&](double v) {
-    v = warp_sum(v);
-    if (l == 0) sh[w] = v;
+  auto norm2 = [&](const double* v) {
+    double a = 0.0;
+    for (int j = tid; j < n; j += 1024) a = fma(v[j], v[j], a);
+    a = warp_sum(a);
+    if (l == 0) sh[w] = a;
     __syncthreads();
-    if (tid == 0) { double t = 0; for (int i = 0; i < 8; i++) t += sh[i]; s_dot = t; }
+    if (tid == 0) { double t = 0; for (int i = 0; i < 32; i++) t += sh[i]; s_nn = t; }
     __syncthreads();
-    return s_dot;
+    return s_nn;
+  };
+  auto cgs_pass = [&](double* vz, int z) {
+    for (int r = w; r < z; r += 32) {
+      const double* vr = VT + (int64_t)r * ldvt;
+      double d = 0.0;
+      for (int j = l; j < n; j += 32) d = fma(vz[j], vr[j], d);
+      d = warp_sum(d);
+      if (l == 0) dots[r] = d;
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += 1024) {
+      double a0 = 0.0, a1 = 0.0;
+      int r = 0;
+      for (; r + 1 < z; r += 2) { a0 = fma(dots[r], VT[(int64_t)r * ldvt + j], a0); a1 = fma(dots[r + 1], VT[(int64_t)(r + 1) * ldvt + j], a1); }
+      if (r < z) a0 = fma(dots[r], VT[(int64_t)r * ldvt + j], a0);
+      vz[j] -= a0 + a1;
+    }
+    __syncthreads();
   };
   int cand = 0;
+  const double thr = 0.5 / (double)n;
   for (int z = 0; z < n; z++) {
     if (S[z] > fl[1]) continue;          // rows are sorted: the (numerically) zero ones are at the end, earlier rows are complete
     double* vz = VT + (int64_t)z * ldvt;
     for (; cand < n; cand++) {
-      for (int j = tid; j < n; j += 256) vz[j] = (j == cand) ? 1.0 : 0.0;
+      for (int j = tid; j < n; j += 1024) vz[j] = (j == cand) ? 1.0 : 0.0;
       __syncthreads();
+      cgs_pass(vz, z);
+      double nn = norm2(vz);
+      if (!(nn > thr)) continue;
       for (int pass = 0; pass < 2; pass++) {
-        for (int r = 0; r < z; r++) {
-          const double* vr = VT + (int64_t)r * ldvt;
-          double d = 0.0;
-          for (int j = tid; j < n; j += 256) d += vz[j] * vr[j];
-          d = bsum(d);
-          for (int j = tid; j < n; j += 256) vz[j] -= d * vr[j];
-          __syncthreads();
-        }
-      }
-      double nn = 0.0;
-      for (int j = tid; j < n; j += 256) nn += vz[j] * vz[j];
-      nn = bsum(nn);
-      if (tid == 0) s_ok = nn > 0.25;
-      __syncthreads();
-      if (s_ok) {
         const double inv = 1.0 / sqrt(nn);
-        for (int j = tid; j < n; j += 256) vz[j] *= inv;
+        for (int j = tid; j < n; j += 1024) vz[j] *= inv;
         __syncthreads();
-        cand++;
-        break;
+        cgs_pass(vz, z);
+        nn = norm2(vz);
       }
+      const double inv = 1.0 / sqrt(nn);
+      for (int j = tid; j < n; j += 1024) vz[j] *= inv;
+      __syncthreads();
+      cand++;
+      break;
     }
   }
 }
@@ -448,7 +466,7 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   PL_LAUNCH_CHECK();
   count_launches(2);
   {   // fill the rows of V^T that belong to exactly zero singular values
-    svd_complete_kernel<<<1, 256, 0, st>>>(VT, ldvt, S, ni, fl);
+    svd_complete_kernel<<<1, 1024, (size_t)ni * sizeof(double), st>>>(VT, ldvt, S, ni, fl);
     PL_LAUNCH_CHECK();
   }
   if (async_path) {

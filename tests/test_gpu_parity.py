@@ -118,6 +118,9 @@ def test_pod_run_remove_mean_against_oracle(pl, m, n):
     # centred data is rank deficient (rows sum to zero): the basis must still be orthonormal
     Uh = host(U)
     assert np.abs(Uh.T @ Uh - np.eye(n)).max() <= 1e-12
+    # ... and so must V (LAPACK completes the null direction of V^T to an orthonormal set; so does svd_complete_kernel)
+    Vh = host(V)
+    assert np.abs(Vh @ Vh.T - np.eye(n)).max() <= 1e-12
     for r in (1e-6, 5, -0.9):
         Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=r)
         Xr = host(pl.POD.reconstruct(Ur, Sr, Vr))

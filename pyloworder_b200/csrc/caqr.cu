@@ -892,10 +892,12 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) caqr_update2_kernel(UpdArgs 
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int r = 16 * (a >> 1) + 4 * t + 2 * h + (a & 1);
+          // T is upper triangular: its block (reflectors 16..31) x (reflectors 0..15) is zero
           double2 b[2];
-          lds_v2(b[0], sT + toff(r, g)); lds_v2(b[1], sT + toff(r, 8 + g));
+          if (a < 2) lds_v2(b[0], sT + toff(r, g));
+          lds_v2(b[1], sT + toff(r, 8 + g));
 #pragma unroll
-          for (int pr = 0; pr < 2; pr++) {
+          for (int pr = (a < 2 ? 0 : 1); pr < 2; pr++) {
             mma884u(wp[2 * pr], w[a][h], b[pr].x);
             mma884u(wp[2 * pr + 1], w[a][h], b[pr].y);
           }
@@ -903,20 +905,23 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) caqr_update2_kernel(UpdArgs 
     } else {
 #pragma unroll
       for (int pr = 0; pr < 2; pr++) {
+        // rows 16..31 of T have no entries in columns 0..15: the accumulators a2 >= 2 skip pr == 0
+        const int na = (pr == 0) ? 2 : 4;
         double2 b0[4], b1[4];
 #pragma unroll
         for (int a2 = 0; a2 < 4; a2++) {
+          if (a2 >= na) continue;
           const int r = 16 * (a2 >> 1) + 2 * g + (a2 & 1);
           lds_v2(b0[a2], sT + toff(r, 8 * pr + 2 * t)); lds_v2(b1[a2], sT + toff(r, 8 * pr + 2 * t + 1));
         }
 #pragma unroll
-        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr][0], b0[a2].x);
+        for (int a2 = 0; a2 < 4; a2++) if (a2 < na) mma884u(wp[a2], w[2 * pr][0], b0[a2].x);
 #pragma unroll
-        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr + 1][0], b0[a2].y);
+        for (int a2 = 0; a2 < 4; a2++) if (a2 < na) mma884u(wp[a2], w[2 * pr + 1][0], b0[a2].y);
 #pragma unroll
-        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr][1], b1[a2].x);
+        for (int a2 = 0; a2 < 4; a2++) if (a2 < na) mma884u(wp[a2], w[2 * pr][1], b1[a2].x);
 #pragma unroll
-        for (int a2 = 0; a2 < 4; a2++) mma884u(wp[a2], w[2 * pr + 1][1], b1[a2].y);
+        for (int a2 = 0; a2 < 4; a2++) if (a2 < na) mma884u(wp[a2], w[2 * pr + 1][1], b1[a2].y);
       }
     }
 #pragma unroll

@@ -567,6 +567,24 @@ def test_two_gpu_nccl_parity():
     assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_c_abi_two_ranks_no_torch(tmp_path):
+    """tests/c_abi_dist.c: two processes (one per GPU), no Python and no torch, through pl_get_unique_id /
+    pl_comm_init_rank / pl_tsqr_svd_host_dist_f64 -- the one-call collective that replaces the reference's dtsqr_svd
+    (pyLOM/vmmath/src/svd.c:678-712) on P ranks.  Compiled here with gcc against include/pylom_b200.h."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "pyloworder_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "c_abi_dist")
+    cc = subprocess.run(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "c_abi_dist.c"), "-o", exe,
+                         "-L" + libdir, "-lpylom_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                         "-Wl,-rpath," + libdir + ",-rpath," + os.path.join(cuda, "lib64")], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "C_ABI_DIST PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_shape_fuzz(pl):
     """Random (m, n) including tile / block / panel boundary cases: invariants against numpy."""
     rng = np.random.default_rng(123)

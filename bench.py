@@ -511,7 +511,7 @@ def run_ours(args):
         traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "caqr_update_kernel (FP64 DMMA)", "achieved": ach, "peak": PEAK_FP64_TFLOPS,
+    roofline = {"bound": "tensor", "kernel": "caqr_update2_kernel (FP64 DMMA, m8n8k4)", "achieved": ach, "peak": PEAK_FP64_TFLOPS,
                 "unit": "TFLOP/s", "frac": ach / PEAK_FP64_TFLOPS,
                 "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/r01_dgemm_peak.json); MEASURED_PEAKS.json has no FP64 entry",
                 "avg_launch_ms": upd_ms / max(upd_launch, 1), "launches_per_step": upd_launch,

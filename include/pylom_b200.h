@@ -54,6 +54,12 @@ int pl_matmul_f64(double* C, int64_t ldc, const double* A, int64_t lda, const do
 size_t pl_matmul_tn_workspace_bytes(int64_t a, int64_t b);
 int pl_matmul_tn_f64(double* C, int64_t ldc, const double* X, int64_t ldx, int64_t a, const double* Y, int64_t ldy,
                      int64_t b, int64_t m, void* ws, size_t ws_bytes, void* stream);
+/* fp32 callers (the reference's float variants stsqr_svd / stemporal_mean ..., pyLOM/vmmath/src/svd.c:416-563,
+ * averaging.c:18-27): the Python layer widens fp32 inputs to fp64 on the device with these two streaming kernels, runs
+ * the fp64 path and narrows the results, so fp32 callers get fp32 arrays back (computed more accurately than sgeqrf would). */
+int pl_widen_f32_f64(double* dst, const float* src, int64_t count, void* stream);
+int pl_narrow_f64_f32(float* dst, const double* src, int64_t count, void* stream);
+
 /* replaces dvecmat(double *v, double *A, m, n): C[i,:] = v[i] A[i,:] (out of place)  vector_matrix.c:401-414 */
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream);
 

@@ -25,6 +25,9 @@ def _host(x):
 
 def _out(x, kind, device):
     """Small results follow the array kind of the input (numpy in -> numpy out, device tensor in -> device tensor)."""
+    if kind.endswith("|f32"):            # float32 caller: small results in single precision too
+        kind = kind[:-4]
+        x = np.asarray(x).astype(np.complex64 if np.iscomplexobj(x) else np.float32)
     if kind == "numpy":
         return x
     t = torch.from_numpy(np.ascontiguousarray(x))

@@ -50,12 +50,11 @@ def truncate(U, S, V, r=1e-8):
 def reconstruct(U, S, V):
     """X(m_i, n) = U(m_i, N) diag(S) V(N, n); the temporal mean is NOT re-added (POD/wrapper.py:86-103)."""
     kind = "torch"
-    if not (isinstance(U, torch.Tensor) and U.is_cuda):
+    keep = lambda t: isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64   # fp64 device views: zero copy
+    if not keep(U):
         U, kind = _dev.to_device(U, "U")
     Sd, _ = _dev.to_device(S, "S")
-    Vd = V if (isinstance(V, torch.Tensor) and V.is_cuda) else _dev.to_device(V, "V")[0]
-    if U.dtype != torch.float64 or Vd.dtype != torch.float64:
-        raise NotImplementedError("only float64 is implemented on the B200 path")
+    Vd = V if keep(V) else _dev.to_device(V, "V")[0]
     if U.stride(1) != 1 and U.shape[1] > 1:
         U = U.contiguous()
     if Vd.stride(1) != 1 and Vd.shape[1] > 1:

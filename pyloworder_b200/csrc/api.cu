@@ -239,6 +239,14 @@ int pl_matmul_tn_f64(double* C, int64_t ldc, const double* X, int64_t ldx, int64
   }
   return gemm_tn(C, ldc, X, ldx, a, Y, ldy, b, m, static_cast<double*>(ws), (cudaStream_t)stream);
 }
+int pl_widen_f32_f64(double* dst, const float* src, int64_t count, void* stream) {
+  if (!dst || !src || count < 0) { set_error("pl_widen_f32_f64: bad arguments"); return -1; }
+  return widen_f32(dst, src, count, (cudaStream_t)stream);
+}
+int pl_narrow_f64_f32(float* dst, const double* src, int64_t count, void* stream) {
+  if (!dst || !src || count < 0) { set_error("pl_narrow_f64_f32: bad arguments"); return -1; }
+  return narrow_f64(dst, src, count, (cudaStream_t)stream);
+}
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream) {
   return vecmat(C, n, v, A, n, m, n, (cudaStream_t)stream);
 }

@@ -150,6 +150,51 @@ int copy_pad(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m
   return launch_row<ROW_COPY>(dst, ldd, src, lds, nullptr, nullptr, m, n, pad_to, st);
 }
 
+// ---- fp32 <-> fp64 streaming conversion (the fp32 entry points of the Python layer compute in fp64) ----------------
+__global__ void __launch_bounds__(256) widen_kernel(double* __restrict__ dst, const float* __restrict__ src, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t n4 = count >> 2;
+    for (int64_t k = i; k < n4; k += stride) {
+      const float4 v = reinterpret_cast<const float4*>(src)[k];
+      reinterpret_cast<double2*>(dst)[2 * k] = make_double2((double)v.x, (double)v.y);
+      reinterpret_cast<double2*>(dst)[2 * k + 1] = make_double2((double)v.z, (double)v.w);
+    }
+    for (int64_t k = 4 * n4 + i; k < count; k += stride) dst[k] = (double)src[k];
+  } else {
+    for (int64_t k = i; k < count; k += stride) dst[k] = (double)src[k];
+  }
+}
+__global__ void __launch_bounds__(256) narrow_kernel(float* __restrict__ dst, const double* __restrict__ src, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t n4 = count >> 2;
+    for (int64_t k = i; k < n4; k += stride) {
+      const double2 a = reinterpret_cast<const double2*>(src)[2 * k], b = reinterpret_cast<const double2*>(src)[2 * k + 1];
+      reinterpret_cast<float4*>(dst)[k] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+    }
+    for (int64_t k = 4 * n4 + i; k < count; k += stride) dst[k] = (float)src[k];
+  } else {
+    for (int64_t k = i; k < count; k += stride) dst[k] = (float)src[k];
+  }
+}
+int widen_f32(double* dst, const float* src, int64_t count, cudaStream_t st) {
+  if (count <= 0) return 0;
+  int64_t blocks = ceil_div(count, 256 * 8); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  widen_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, src, count);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+int narrow_f64(float* dst, const double* src, int64_t count, cudaStream_t st) {
+  if (count <= 0) return 0;
+  int64_t blocks = ceil_div(count, 256 * 8); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  narrow_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, src, count);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- vecmat: C[i,:] = v[i] * A[i,:] --------------------------------------------------------
 __global__ void vecmat_kernel(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -33,7 +33,7 @@ def dev(x):
 
 
 def host(t):
-    return t.cpu().numpy()
+    return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
 def assert_svd_parity(ref, got, n_expected=None):
@@ -219,6 +219,31 @@ def test_qr_and_svd_entry_points(pl):
     assert np.max(np.abs(S - So) / So) <= 1e-10
 
 
+@pytest.mark.parametrize("container", ["torch", "numpy"])
+def test_float32_inputs(pl, container):
+    """float32 callers (the reference's `real` fused type covers float: stsqr_svd, pyLOM/vmmath/src/svd.c:529-563): inputs are
+    widened on the device, the fp64 path runs, results come back as float32.  Compared with the oracle run on the
+    same (float32-valued) data; tolerances are single-precision ones."""
+    X32 = synth.snapshots(20000, 48, 77).astype(np.float32)
+    Xin = torch.from_numpy(X32).cuda() if container == "torch" else X32
+    U, S, V = pl.POD.run(Xin, remove_mean=True)
+    assert (U.dtype, S.dtype, V.dtype) == ((torch.float32,) * 3 if container == "torch" else (np.float32,) * 3)
+    Uo, So, Vo = po.pod_run(X32.astype(np.float64), remove_mean=True)
+    Uh, Sh, Vh = [np.asarray(host(t), dtype=np.float64) for t in (U, S, V)]
+    assert np.abs(Sh - So).max() <= 2e-7 * So[0]
+    big = So / So[0] >= 1e-3
+    gaps = np.minimum(np.r_[np.inf, -np.diff(So)], np.r_[-np.diff(So), np.inf]) / So[0] >= 1e-3
+    sel = big & gaps
+    assert np.abs(np.einsum("ik,ik->k", Uo, Uh))[sel].min() >= 1 - 1e-5
+    Ur, Sr, Vr = pl.POD.truncate(U, S, V, r=5)
+    Xr = pl.POD.reconstruct(Ur, Sr, Vr)
+    assert Xr.dtype == U.dtype and tuple(Xr.shape) == X32.shape
+    mean = pl.math.temporal_mean(Xin)
+    assert mean.dtype == U.dtype and np.abs(np.asarray(host(mean), dtype=np.float64) - X32.astype(np.float64).mean(1)).max() <= 1e-6
+    with pytest.raises(NotImplementedError):
+        pl.math.tsqr_svd(torch.zeros((64, 4), dtype=torch.complex128, device="cuda"))
+
+
 def test_exactly_rank_deficient_input(pl):
     """All-zero trailing snapshot columns give exactly zero singular values; U and V must stay orthonormal
     (LAPACK returns an arbitrary orthonormal completion, so only the invariants are compared)."""
@@ -240,7 +265,7 @@ def test_error_behaviour(pl):
     with pytest.raises(ValueError, match="at least n rows"):
         pl.math.tsqr_svd(dev(np.zeros((3, 5))))
     with pytest.raises(NotImplementedError):
-        pl.math.tsqr_svd(torch.zeros((10, 2), dtype=torch.float32, device="cuda"))
+        pl.math.tsqr_svd(torch.zeros((10, 2), dtype=torch.complex64, device="cuda"))     # float32 is accepted (widened)
     with pytest.raises(ValueError, match="1 <= r <= n"):
         pl.POD.run(dev(np.ones((10, 2))), randomized=True, r=3)
     from pyloworder_b200 import _lib

@@ -66,6 +66,18 @@ def test_truncation_rule(path):
         assert po.compute_truncation_residual(S, float(r)) == int(N)
 
 
+def test_worksplit_matches_the_reference_function():
+    """tests/golden/aux/worksplit_ref.npz holds the outputs of the reference's own `worksplit` source
+    (pyLOM/utils/parall.py:24-48, executed verbatim by oracle/gen_worksplit_golden.py): the oracle's restatement and the
+    product's utils.worksplit must reproduce every entry (the golden row splits of gen_golden.py use the oracle's)."""
+    tab = np.load(os.path.join(os.path.dirname(__file__), "golden", "aux", "worksplit_ref.npz"))["table"]
+    assert len(tab) > 500
+    import pyloworder_b200.utils as plu
+    for i0, i1, rank, size, a, b in tab.tolist():
+        assert tuple(po.worksplit(i0, i1, rank, size)) == (a, b), (i0, i1, rank, size)
+        assert tuple(plu.worksplit(i0, i1, rank, size)) == (a, b), (i0, i1, rank, size)
+
+
 def test_worksplit_covers_range():
     for m, P in ((10, 3), (89351, 8), (7, 7), (5, 8), (1000, 1)):
         edges = [po.worksplit(0, m, r, P) for r in range(P)]

@@ -60,6 +60,13 @@ int pl_matmul_tn_f64(double* C, int64_t ldc, const double* X, int64_t ldx, int64
 int pl_widen_f32_f64(double* dst, const float* src, int64_t count, void* stream);
 int pl_narrow_f64_f32(float* dst, const double* src, int64_t count, void* stream);
 
+/* complex128 callers (ztsqr_svd, pyLOM/vmmath/src/svd.c:714-1010; SPOD, pyLOM/SPOD/wrapper.py:80-86): the Python layer
+ * factors the real embedding Ahat = [[Ar, -Ai], [Ai, Ar]] (2m x 2n) with the fp64 path and keeps one member of every
+ * pair of equal singular values.  pl_complex_embed_f64 builds Ahat from the interleaved complex matrix A (m x n);
+ * pl_complex_pack_f64 writes Uc (m x n complex) = (P_top - Q_bot) + i (Q_top + P_bot) for 2m x n real P, Q (Q may be NULL). */
+int pl_complex_embed_f64(double* Ahat, const double* A, int64_t m, int64_t n, void* stream);
+int pl_complex_pack_f64(double* Uc, const double* P, const double* Q, int64_t m, int64_t n, void* stream);
+
 /* replaces dvecmat(double *v, double *A, m, n): C[i,:] = v[i] A[i,:] (out of place)  vector_matrix.c:401-414 */
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream);
 

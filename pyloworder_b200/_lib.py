@@ -29,6 +29,8 @@ _SIGS = {
     "pl_vecmat_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pl_widen_f32_f64": (_int, [_vp, _vp, _i64, _vp]),
     "pl_narrow_f64_f32": (_int, [_vp, _vp, _i64, _vp]),
+    "pl_complex_embed_f64": (_int, [_vp, _vp, _i64, _i64, _vp]),
+    "pl_complex_pack_f64": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pl_rmse_workspace_bytes": (_sz, []),
     "pl_rmse_sums_f64": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "pl_qr_workspace_bytes": (_sz, [_i64, _i64]),

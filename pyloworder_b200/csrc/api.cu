@@ -247,6 +247,14 @@ int pl_narrow_f64_f32(float* dst, const double* src, int64_t count, void* stream
   if (!dst || !src || count < 0) { set_error("pl_narrow_f64_f32: bad arguments"); return -1; }
   return narrow_f64(dst, src, count, (cudaStream_t)stream);
 }
+int pl_complex_embed_f64(double* Ahat, const double* A, int64_t m, int64_t n, void* stream) {
+  if (!Ahat || !A || m < 0 || n < 0) { set_error("pl_complex_embed_f64: bad arguments"); return -1; }
+  return complex_embed(Ahat, A, m, n, (cudaStream_t)stream);
+}
+int pl_complex_pack_f64(double* Uc, const double* P, const double* Q, int64_t m, int64_t n, void* stream) {
+  if (!Uc || !P || m < 0 || n < 0) { set_error("pl_complex_pack_f64: bad arguments"); return -1; }
+  return complex_pack(Uc, P, Q, m, n, (cudaStream_t)stream);
+}
 int pl_vecmat_f64(double* C, const double* v, const double* A, int64_t m, int64_t n, void* stream) {
   return vecmat(C, n, v, A, n, m, n, (cudaStream_t)stream);
 }

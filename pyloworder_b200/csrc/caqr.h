@@ -62,6 +62,8 @@ int center_var_rows(double* Y, int64_t ldy, double* mean, double* var, const dou
 int copy_pad(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t m, int64_t n, int64_t pad_to, cudaStream_t st);
 int widen_f32(double* dst, const float* src, int64_t count, cudaStream_t st);
 int narrow_f64(float* dst, const double* src, int64_t count, cudaStream_t st);
+int complex_embed(double* Ah, const double* A, int64_t m, int64_t n, cudaStream_t st);
+int complex_pack(double* Uc, const double* P, const double* Q, int64_t m, int64_t n, cudaStream_t st);
 int vecmat(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n, cudaStream_t st);
 int sumsq_diff(double* out2, double* scratch, const double* A, const double* B, int64_t cnt, cudaStream_t st);
 constexpr int SUMSQ_SCRATCH_DOUBLES = 2 * 148 * 4;

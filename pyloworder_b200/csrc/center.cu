@@ -195,6 +195,42 @@ int narrow_f64(float* dst, const double* src, int64_t count, cudaStream_t st) {
   return 0;
 }
 
+// ---- complex <-> real embedding (complex128 tsqr_svd runs as a real SVD of [[Ar, -Ai], [Ai, Ar]]) -------------------
+// Ahat (2m x 2n, row major) from A (m x n complex, interleaved re/im)
+__global__ void __launch_bounds__(256) complex_embed_kernel(double* __restrict__ Ah, const double2* __restrict__ A, int64_t m, int64_t n) {
+  const int64_t tot = m * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / n, j = idx - i * n;
+    const double2 a = A[idx];
+    Ah[i * 2 * n + j] = a.x;           Ah[i * 2 * n + n + j] = -a.y;
+    Ah[(m + i) * 2 * n + j] = a.y;     Ah[(m + i) * 2 * n + n + j] = a.x;
+  }
+}
+// Uc (m x n complex) = (P_top - Q_bot) + i (Q_top + P_bot); P, Q are 2m x n real, Q may be null (zero)
+__global__ void __launch_bounds__(256) complex_pack_kernel(double2* __restrict__ Uc, const double* __restrict__ P, const double* __restrict__ Q,
+                                                           int64_t m, int64_t n) {
+  const int64_t tot = m * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    double re = P[idx], im = P[tot + idx];
+    if (Q) { re -= Q[tot + idx]; im += Q[idx]; }
+    Uc[idx] = make_double2(re, im);
+  }
+}
+int complex_embed(double* Ah, const double* A, int64_t m, int64_t n, cudaStream_t st) {
+  if (m * n <= 0) return 0;
+  int64_t blocks = ceil_div(m * n, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  complex_embed_kernel<<<(unsigned)blocks, 256, 0, st>>>(Ah, reinterpret_cast<const double2*>(A), m, n);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+int complex_pack(double* Uc, const double* P, const double* Q, int64_t m, int64_t n, cudaStream_t st) {
+  if (m * n <= 0) return 0;
+  int64_t blocks = ceil_div(m * n, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  complex_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<double2*>(Uc), P, Q, m, n);
+  PL_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- vecmat: C[i,:] = v[i] * A[i,:] --------------------------------------------------------
 __global__ void vecmat_kernel(double* C, int64_t ldc, const double* v, const double* A, int64_t lda, int64_t m, int64_t n) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

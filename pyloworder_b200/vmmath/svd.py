@@ -233,9 +233,90 @@ def _tsqr_svd_dev(Ad, center=False, engine=None):
     return U, S, VT, mean
 
 
+def _complex_select(S2, V2, n):
+    """Host part of the complex path (2n numbers / a 2n x 2n matrix).  The real embedding doubles every singular value;
+    the right vectors [c; d] of a cluster of 2k equal values span, as complex vectors c + i d, a k-dimensional complex
+    space (v and i v are both in it).  Per cluster keep the k vectors picked by pivoted complex Gram-Schmidt (largest
+    residual first), then orthonormalise the kept set: the correction M is the identity up to rounding unless complex
+    singular values coincide (k > 1: repeated values, several zeros).  Returns the kept indices J (n, ascending), M
+    (n x n complex, None when |M - I| <= 1e-12) and the orthonormal complex right vectors as the columns of X."""
+    Vc = V2[:, :n] + 1j * V2[:, n:]                 # row j: v_j^T as a complex row
+    tol = 1e-10 * max(float(S2[0]), 1e-300)
+    J = []
+    j0 = 0
+    while j0 < 2 * n:
+        j1 = j0 + 1
+        while j1 < 2 * n and (abs(S2[j1] - S2[j0]) <= tol or (j1 - j0) % 2 == 1):   # clusters have an even number of members
+            j1 += 1
+        k = (j1 - j0) // 2
+        cand = Vc[j0:j1].copy()                      # residuals, updated in place
+        for _ in range(k):
+            nrm = _np.einsum("ij,ij->i", cand.conj(), cand).real
+            p = int(_np.argmax(nrm))
+            J.append(j0 + p)
+            q = cand[p] / _np.sqrt(nrm[p])
+            cand = cand - _np.outer(cand @ q.conj(), q)
+            cand[p] = 0.0
+        j0 = j1
+    J = _np.array(sorted(J))
+    if len(J) != n:
+        raise RuntimeError("complex tsqr_svd: could not separate the doubled singular pairs of the real embedding")
+    X = Vc[J].T                                      # columns v_k
+    Qx, Rx = _np.linalg.qr(X)
+    ph = _np.diag(Rx) / _np.abs(_np.diag(Rx))        # keep the phases of the kept vectors
+    M = _np.linalg.inv(Rx) * ph[None, :]
+    if _np.abs(M - _np.eye(n)).max() <= 1e-12:
+        return J, None, X
+    return J, M, Qx * ph[None, :]
+
+
+def _tsqr_svd_complex(Ac):
+    """complex128 tsqr_svd (ztsqr_svd, pyLOM/vmmath/src/svd.c:955-1010; the call of SPOD, pyLOM/SPOD/wrapper.py:83): the fp64 path on
+    the real embedding Ahat = [[Ar, -Ai], [Ai, Ar]] of the local shard (a row permutation of the global embedding, which
+    does not change S, V and permutes U accordingly).  Ahat = Qhat Rhat (TSQR, explicit Qhat), Rhat = Ur diag(S2) V2^T
+    (Jacobi, 2n x 2n), every complex singular triplet appears twice; keep one member per pair:
+    U = Qhat Ur[:, J] read as top + i bottom, S = S2[J], V^H rows = conj(c + i d) of the kept rows [c; d] of V2^T.
+    Costs twice the flops and memory of a native complex factorisation."""
+    L = _lib.lib()
+    Ac = Ac.contiguous()
+    m, n = Ac.shape
+    Ahat = torch.empty((2 * m, 2 * n), dtype=torch.float64, device=Ac.device)
+    _lib.check(L.pl_complex_embed_f64(Ahat.data_ptr(), Ac.data_ptr(), m, n, _dev.stream()), "complex_embed")
+    Qh, Rh = _tsqr_dev(Ahat)
+    del Ahat
+    Urh, S2, VT2 = _engine.svd(Rh.contiguous())
+    J, M, X = _complex_select(S2.cpu().numpy(), VT2.cpu().numpy(), n)
+    Jd = torch.from_numpy(J).to(Ac.device)
+    W = Urh.index_select(1, Jd).contiguous()                     # (2n, n) column gather of the small factor
+    U = torch.empty((m, n), dtype=torch.complex128, device=Ac.device)
+    if M is None:
+        P = _engine.matmul(Qh, W)
+        _lib.check(L.pl_complex_pack_f64(U.data_ptr(), P.data_ptr(), 0, m, n, _dev.stream()), "complex_pack")
+    else:                                                        # coinciding complex singular values: U <- U M
+        Md = torch.from_numpy(_np.ascontiguousarray(M)).to(Ac.device)
+        Uh = _engine.matmul(Qh, W)                               # [Ur; Ui]
+        P = _engine.matmul(Uh, Md.real.contiguous())
+        Q = _engine.matmul(Uh, Md.imag.contiguous())
+        _lib.check(L.pl_complex_pack_f64(U.data_ptr(), P.data_ptr(), Q.data_ptr(), m, n, _dev.stream()), "complex_pack")
+    S = S2.index_select(0, Jd).contiguous()
+    VH = torch.from_numpy(_np.ascontiguousarray(X.conj().T)).to(Ac.device)     # rows v_k^H: A = U diag(S) VH
+    return U, S, VH
+
+
 @cr('math.tsqr_svd')
 def tsqr_svd(Ai):
-    """SVD of the row-distributed matrix via TSQR.  Ai(m_i,n) -> Ui(m_i,n), S(n), V(n,n) = V^T."""
+    """SVD of the row-distributed matrix via TSQR.  Ai(m_i,n) -> Ui(m_i,n), S(n), V(n,n) = V^T (V^H for complex input)."""
+    if (isinstance(Ai, torch.Tensor) and Ai.dtype == torch.complex128) or (isinstance(Ai, _np.ndarray) and Ai.dtype == _np.complex128):
+        _dev.require_cuda()
+        is_np = isinstance(Ai, _np.ndarray)
+        Ac = torch.from_numpy(_np.ascontiguousarray(Ai)) if is_np else Ai
+        on_host = not Ac.is_cuda
+        if Ac.dim() != 2:
+            raise ValueError("expected a 2-D array (m, n)")
+        U, S, VH = _tsqr_svd_complex(Ac.cuda() if on_host else Ac)
+        if is_np:
+            return U.cpu().numpy(), S.cpu().numpy(), VH.cpu().numpy()
+        return (U.cpu(), S.cpu(), VH.cpu()) if on_host else (U, S, VH)
     Ad, kind = _dev.to_device(Ai, "Ai")
     U, S, VT, _ = _tsqr_svd_dev(Ad)
     return _dev.from_device(U, kind), _dev.from_device(S, kind), _dev.from_device(VT, kind)

@@ -241,7 +241,40 @@ def test_float32_inputs(pl, container):
     mean = pl.math.temporal_mean(Xin)
     assert mean.dtype == U.dtype and np.abs(np.asarray(host(mean), dtype=np.float64) - X32.astype(np.float64).mean(1)).max() <= 1e-6
     with pytest.raises(NotImplementedError):
-        pl.math.tsqr_svd(torch.zeros((64, 4), dtype=torch.complex128, device="cuda"))
+        pl.math.tsqr_svd(torch.zeros((64, 4), dtype=torch.complex64, device="cuda"))
+
+
+@pytest.mark.parametrize("case", ["generic", "repeated", "deficient", "numpy"])
+def test_complex_tsqr_svd(pl, case):
+    """complex128 tsqr_svd (the call of SPOD, pyLOM/SPOD/wrapper.py:83; ztsqr_svd src/svd.c:955-1010) through the real
+    embedding: singular values against LAPACK, modes up to a complex phase, U^H U = I, A = U S V^H."""
+    rng = np.random.default_rng(5)
+    m, n = 6000, 24
+    if case in ("generic", "numpy"):
+        A = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+        A *= 10.0 ** (-3.0 * np.arange(n) / n)
+    else:
+        Q, _ = np.linalg.qr(rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n)))
+        W, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+        sv = np.linspace(3.0, 1.0, n)
+        sv[5] = sv[4]; sv[11] = sv[10] = sv[9]                       # coinciding complex singular values
+        if case == "deficient":
+            sv[-3:] = 0.0
+        A = (Q * sv) @ W.conj().T
+    Ain = A if case == "numpy" else torch.from_numpy(A).cuda()
+    U, S, VH = pl.math.tsqr_svd(Ain)
+    U, S, VH = [np.asarray(host(t)) for t in (U, S, VH)]
+    assert U.shape == (m, n) and S.shape == (n,) and VH.shape == (n, n) and np.iscomplexobj(U) and np.iscomplexobj(VH)
+    So = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(S - So).max() <= 1e-12 * So[0]
+    assert np.abs(VH @ VH.conj().T - np.eye(n)).max() <= 1e-11
+    assert np.abs((U * S) @ VH - A).max() <= 1e-11 * np.abs(A).max()
+    nz = So > 1e-9 * So[0]
+    G = U[:, nz].conj().T @ U[:, nz]
+    assert np.abs(G - np.eye(int(nz.sum()))).max() <= 1e-10
+    if case in ("generic", "numpy"):
+        Uo = np.linalg.svd(A, full_matrices=False)[0]
+        assert np.abs(np.einsum("ik,ik->k", Uo.conj(), U)).min() >= 1 - 1e-8
 
 
 def test_exactly_rank_deficient_input(pl):

@@ -124,6 +124,23 @@ for (m, n) in ((30000, 64), (9000, 33)):
     ok &= bool(good)
     if rank == 0:
         print(f"P={size} host phase calls {m}x{n}: rc={rc} sigma_rel={sig:.2e} mode_min={ipn[sel].min():.12f} orth={orth:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+# ---- complex128 tsqr_svd (real embedding of every rank's shard; SPOD's call) against LAPACK on the whole matrix
+for (m, n) in ((8000, 12),):
+    rng = np.random.default_rng(9)
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) * 10.0 ** (-2.0 * np.arange(n) / n)
+    r0, r1 = pl.utils.worksplit(0, m, rank, size)
+    U, S, VH = pl.math.tsqr_svd(torch.from_numpy(A[r0:r1].copy()).to(dev))
+    Uo, So, VHo = np.linalg.svd(A, full_matrices=False)
+    sig = np.abs(S.cpu().numpy() - So).max() / So[0]
+    ip = torch.view_as_real(torch.from_numpy(np.einsum("ik,ik->k", Uo[r0:r1].conj(), U.cpu().numpy())).to(dev).contiguous())
+    dist.all_reduce(ip)
+    ipn = np.abs(torch.view_as_complex(ip).cpu().numpy())
+    rec = torch.tensor([np.abs((U.cpu().numpy() * S.cpu().numpy()) @ VH.cpu().numpy() - A[r0:r1]).max()], device=dev)
+    dist.all_reduce(rec, op=dist.ReduceOp.MAX)
+    good = sig <= 1e-12 and ipn.min() >= 1 - 1e-8 and float(rec) <= 1e-11 * np.abs(A).max()
+    ok &= bool(good)
+    if rank == 0:
+        print(f"P={size} complex tsqr_svd {m}x{n}: sigma_rel={sig:.2e} mode_min={ipn.min():.12f} recon={float(rec):.2e} -> {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)

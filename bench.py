@@ -17,7 +17,7 @@ e2e            = same metric through the host-pointer C ABI call (pl_tsqr_svd_ho
                  drop-in for the reference's dtsqr_svd), host<->device copies inside the timed region
                  (pinned host buffers; the library caches its device buffers after the first call);
                  `pageable` = the same call on plain numpy arrays (N = 1).
-roofline       = dominant kernel of the step (caqr_update_kernel, FP64 DMMA block-reflector application),
+roofline       = dominant kernel of the step (caqr_update2_kernel, FP64 DMMA block-reflector application),
                  per-launch CUDA-event timing from the library's profiling hooks.
 other_configs  = the other BASELINE shapes as per-GPU shards: cfg5 (125,000,000 x 64 tsqr_svd; on 8 GPUs this
                  IS config 5), cfg3 (24,000,000 x 256 POD.run(remove_mean)), cfg4 (2,000,000 x 1000 DMD),
@@ -494,7 +494,7 @@ def run_ours(args):
     L.pl_profile_read(ctypes.cast(msb, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p), NC)
     names = ["copy_center", "panel", "update_factor", "update_formq", "gemm", "svd_small", "misc", "tsqr_small"]
     phases = {names[i]: {"ms": round(msb[i], 3), "launches": int(cnt[i])} for i in range(NC)}
-    # dominant kernel: caqr_update_kernel.  Algorithmic flops of one block-reflector application
+    # dominant kernel: caqr_update2_kernel.  Algorithmic flops of one block-reflector application
     # = 4 * rows * NB * cols (W = V^T C and C -= V W').  Factor pass: cols = trailing columns of each panel;
     # form-Q pass: trailing + own panel columns.
     npad = -(-n // 32) * 32

@@ -252,6 +252,140 @@ __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restr
   sweep_end(rotations);
 }
 
+// Block one-sided Jacobi, second generation: only G is staged in shared memory.  The left rotations of a block round are
+// ACCUMULATED in a small orthogonal matrix Om (2 BR x 2 BR, shared memory; a Givens rotation costs 2 x 2 BR entries
+// instead of 2 n) and applied to the 2 BR rows of J once per round as a dense product J_rows <- Om J_rows read from /
+// written to L2.  Half the shared memory per row means twice the rows per block at a given n (BR = 16 up to n = 512,
+// BR = 8 up to n = 1024): half the block rounds and grid barriers per sweep, half the CTAs on the machine (the sweep
+// launches share the GPU with the Q formation), and the mini-steps touch G only.
+// Rotation that orthogonalises two rows with squared norms a, b and inner product c != 0 (the smaller angle):
+// t = sgn(d) h / (|d| + sqrt(d^2 + h^2)), d = b - a, h = 2 c;  cs = 1 / sqrt(1 + t^2), sn = cs t  -- the same numbers as
+// zeta = d / h, t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), without the two divisions and two square roots of the
+// textbook form (each a ~150-cycle dependent step of every pair): rsqrt / rcp seeds + two Newton steps, like the
+// Householder scalars of the panel kernels.
+__device__ __forceinline__ void jacobi_rotation(double a, double b, double c, double& cs, double& sn) {
+  const double d = b - a, h = 2.0 * c;
+  const double q = fma(d, d, h * h);
+  double y, rc;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+  const double hq = 0.5 * q;
+  y = y * fma(-hq * y, y, 1.5);
+  y = y * fma(-hq * y, y, 1.5);
+  const double den = fabs(d) + q * y;                 // |d| + sqrt(d^2 + h^2) > 0
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+  rc = rc * fma(-den, rc, 2.0);
+  rc = rc * fma(-den, rc, 2.0);
+  const double t = (signbit(d) ? -h : h) * rc;        // sgn(d) h / den   (the sign bit of +-0 counts, like copysign(1, zeta))
+  const double w = fma(t, t, 1.0);
+  double z;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(w));
+  const double hw = 0.5 * w;
+  z = z * fma(-hw * z, z, 1.5);
+  z = z * fma(-hw * z, z, 1.5);
+  cs = z; sn = z * t;
+}
+
+template <int BR, int EPL>
+__global__ void __launch_bounds__(256) jacobi_block_sweep2_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
+                                                                  double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
+  extern __shared__ __align__(16) double jsm[];
+  if (sweep_done(rotations)) return;      // converged in an earlier launch of the fixed sweep budget
+  constexpr int R2 = 2 * BR, LDO = R2 + 1;
+  const double floor2 = fl[0], tol2 = tol * tol;
+  double* Gs = jsm;                       // [R2][n]
+  double* Om = jsm + (size_t)R2 * n;      // [R2][LDO]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i = blockIdx.x;
+  for (int round = 0; round < nbe - 1; round++) {
+    int bp, bq;
+    if (i == 0) { bp = nbe - 1; bq = round; }
+    else { bp = (round + i) % (nbe - 1); bq = (round - i + (nbe - 1)) % (nbe - 1); }
+    if (bp > bq) { int tmp = bp; bp = bq; bq = tmp; }
+    auto grow = [&](int lr) { return lr < BR ? bp * BR + lr : bq * BR + (lr - BR); };
+    // ---- stage the 2*BR rows of G (rows >= n are phantom: zeros, never stored); Om <- I
+    for (int lr = warp; lr < R2; lr += 8) {
+      const int gr = grow(lr);
+      const bool ok = gr < n;
+      double gv[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const int j = lane + 32 * e;
+        gv[e] = (ok && j < n) ? __ldcg(Gm + (int64_t)gr * n + j) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const int j = lane + 32 * e;
+        if (j < n) Gs[(size_t)lr * n + j] = gv[e];
+      }
+    }
+    for (int e = tid; e < R2 * R2; e += 256) Om[(e / R2) * LDO + (e % R2)] = (e / R2 == e % R2) ? 1.0 : 0.0;
+    __syncthreads();
+    const int nmini = (round == 0) ? (R2 - 1) : BR;
+    for (int k = 0; k < nmini; k++) {
+      for (int pw = warp; pw < BR; pw += 8) {
+        int a, b;
+        if (round == 0) {      // round-robin over the 2*BR local rows
+          if (pw == 0) { a = R2 - 1; b = k; }
+          else { a = (k + pw) % (R2 - 1); b = (k - pw + (R2 - 1)) % (R2 - 1); }
+        } else { a = pw; b = BR + (pw + k) % BR; }
+        double* x = Gs + (size_t)a * n; double* y = Gs + (size_t)b * n;
+        double xv[EPL], yv[EPL];
+        double sa = 0, sb = 0, sc = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int j = lane + 32 * e;
+          xv[e] = (j < n) ? x[j] : 0.0; yv[e] = (j < n) ? y[j] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; e++) { sa = fma(xv[e], xv[e], sa); sb = fma(yv[e], yv[e], sb); sc = fma(xv[e], yv[e], sc); }
+        sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc);
+        if (!(sc == 0.0 || sc * sc <= tol2 * (sa * sb) || fmin(sa, sb) <= floor2)) {
+          if (lane == 0) atomicAdd(rotations, 1);
+          double cs, sn;
+          jacobi_rotation(sa, sb, sc, cs, sn);
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int j = lane + 32 * e;
+            if (j < n) { x[j] = cs * xv[e] - sn * yv[e]; y[j] = sn * xv[e] + cs * yv[e]; }
+          }
+          if (lane < R2) {       // the same rotation on rows a, b of Om
+            const double u = Om[a * LDO + lane], v = Om[b * LDO + lane];
+            Om[a * LDO + lane] = cs * u - sn * v; Om[b * LDO + lane] = sn * u + cs * v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- write the rows of G back; J_rows <- Om J_rows (one column per thread and pass, rows of J from / to L2)
+    for (int lr = warp; lr < R2; lr += 8) {
+      const int gr = grow(lr);
+      if (gr < n) {
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int j = lane + 32 * e;
+          if (j < n) Gm[(int64_t)gr * n + j] = Gs[(size_t)lr * n + j];
+        }
+      }
+    }
+    for (int j = tid; j < n; j += 256) {
+      double jo[R2];
+#pragma unroll
+      for (int sidx = 0; sidx < R2; sidx++) { const int gr = grow(sidx); jo[sidx] = gr < n ? __ldcg(J + (int64_t)gr * n + j) : 0.0; }
+#pragma unroll 4
+      for (int r = 0; r < R2; r++) {
+        const int gr = grow(r);
+        if (gr >= n) continue;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int sidx = 0; sidx < R2; sidx += 2) { acc0 = fma(Om[r * LDO + sidx], jo[sidx], acc0); acc1 = fma(Om[r * LDO + sidx + 1], jo[sidx + 1], acc1); }
+        J[(int64_t)gr * n + j] = acc0 + acc1;
+      }
+    }
+    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
+  }
+  sweep_end(rotations);
+}
+
 __global__ void __launch_bounds__(128) row_norm_kernel(double* s, const double* Gm, int n, int64_t ld) {
   __shared__ double sh[3][4];
   const double* g = Gm + (int64_t)blockIdx.x * ld;
@@ -409,19 +543,35 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
     const bool use_coop = coop && ni <= 1024 && sweep_blocks <= nsm;
     // block variant: BR rows per block, 2*BR*n*16 bytes of shared memory per CTA
     int br = 0;
-    if (coop && ni >= 64 && !getenv("PL_JACOBI_ROWPAIR")) {
-      if ((size_t)2 * 8 * ni * 16 <= 200 * 1024) br = 8; else if (ni <= 1024 && (size_t)2 * 4 * ni * 16 <= 200 * 1024) br = 4;
-    }
+    static const bool jac_old = getenv("PL_JACOBI_OLD") != nullptr;          // first-generation block kernel (A/B timing only)
+    static const int br_force = getenv("PL_JACOBI_BR") ? atoi(getenv("PL_JACOBI_BR")) : 0;
     int nbe = 0; size_t bsm = 0; void* bfn = nullptr;
-    if (br) {
+    if (coop && ni >= 64 && !getenv("PL_JACOBI_ROWPAIR") && !jac_old && ni <= 1024) {
+      // second generation: G only in shared memory (2 BR n doubles + Om): BR = 16 up to n = 512, BR = 8 up to n = 1024
+      br = 8;
+      if (br_force == 8 || br_force == 16) br = br_force;
+      if ((size_t)2 * br * ni * 8 > 200 * 1024) br = 8;
       const int nblk = (ni + br - 1) / br;
       nbe = nblk + (nblk & 1);
-      bsm = (size_t)2 * br * ni * 16;
-      if (br == 8) bfn = ni <= 128 ? (void*)jacobi_block_sweep_kernel<8, 4> : ni <= 256 ? (void*)jacobi_block_sweep_kernel<8, 8>
-                       : ni <= 512 ? (void*)jacobi_block_sweep_kernel<8, 16> : (void*)jacobi_block_sweep_kernel<8, 25>;
-      else bfn = (void*)jacobi_block_sweep_kernel<4, 32>;
-      if (nbe / 2 > nsm) br = 0;
+      bsm = (size_t)2 * br * ni * 8 + (size_t)2 * br * (2 * br + 1) * 8;
+      if (br == 16) bfn = ni <= 128 ? (void*)jacobi_block_sweep2_kernel<16, 4> : ni <= 256 ? (void*)jacobi_block_sweep2_kernel<16, 8>
+                        : (void*)jacobi_block_sweep2_kernel<16, 16>;
+      else bfn = ni <= 128 ? (void*)jacobi_block_sweep2_kernel<8, 4> : ni <= 256 ? (void*)jacobi_block_sweep2_kernel<8, 8>
+               : ni <= 512 ? (void*)jacobi_block_sweep2_kernel<8, 16> : (void*)jacobi_block_sweep2_kernel<8, 32>;
+      if (nbe / 2 > nsm || nbe < 2) br = 0;
       else PL_CUDA(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    } else if (coop && ni >= 64 && !getenv("PL_JACOBI_ROWPAIR")) {
+      if ((size_t)2 * 8 * ni * 16 <= 200 * 1024) br = 8; else if (ni <= 1024 && (size_t)2 * 4 * ni * 16 <= 200 * 1024) br = 4;
+      if (br) {
+        const int nblk = (ni + br - 1) / br;
+        nbe = nblk + (nblk & 1);
+        bsm = (size_t)2 * br * ni * 16;
+        if (br == 8) bfn = ni <= 128 ? (void*)jacobi_block_sweep_kernel<8, 4> : ni <= 256 ? (void*)jacobi_block_sweep_kernel<8, 8>
+                         : ni <= 512 ? (void*)jacobi_block_sweep_kernel<8, 16> : (void*)jacobi_block_sweep_kernel<8, 25>;
+        else bfn = (void*)jacobi_block_sweep_kernel<4, 32>;
+        if (nbe / 2 > nsm) br = 0;
+        else PL_CUDA(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+      }
     }
     PL_CUDA(cudaMemsetAsync(state, 0, 4 * sizeof(int), st));
     if (br || use_coop) {

@@ -20,3 +20,14 @@ X = torch.from_numpy(synth.snapshots(6000, 48, 7)).cuda()
 U, S, V = pl.POD.run(X, remove_mean=True); torch.cuda.synchronize()
 I = torch.eye(48, dtype=torch.float64, device=dev)
 print("POD centred: VVt-I", float((V @ V.T - I).abs().max()), flush=True)
+# second-generation Jacobi kernel (phantom rows, odd block counts), fp32 widening, complex embedding
+for n in (65, 100, 151, 250):
+    R = torch.linalg.qr(torch.randn((3 * n, n), dtype=torch.float64, device=dev), mode="r")[1].contiguous()
+    U, S, V = pl.math.svd(R); torch.cuda.synchronize()
+    print("svd", n, float(((U * S) @ V - R).abs().max()), flush=True)
+X32 = torch.randn((5000, 40), dtype=torch.float32, device=dev)
+U, S, V = pl.POD.run(X32, remove_mean=True); torch.cuda.synchronize()
+print("fp32", U.dtype, float(S[0]), flush=True)
+Ac = torch.randn((3000, 10), dtype=torch.complex128, device=dev)
+U, S, VH = pl.math.tsqr_svd(Ac); torch.cuda.synchronize()
+print("complex", float(((U * S) @ VH - Ac).abs().max()), flush=True)

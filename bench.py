@@ -641,6 +641,9 @@ def run_ours(args):
                 "config": workload_config(args.rows, n, size, args.steps, args.warmup),
                 "rows_snapshots_per_s": m_global * n / (ms * 1e-3),
                 "frac_of_fp64_roofline": value * 1e-3 / (PEAK_FP64_TFLOPS * size),
+                # transparency: the formulation executes 6 m n^2 (factor 2 + form Q 2 + GEMM 2) for n > 64
+                "executed": {"flops": "6*m*n^2", "tflops": 1.5 * value * 1e-3, "frac_of_fp64_peak": 1.5 * value * 1e-3 / (PEAK_FP64_TFLOPS * size),
+                             "ceiling_of_frac_of_fp64_roofline": 4.0 / 6.0},
                 "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "phases_ms": phases,
                 "checks": chk, "parity": parity, "other_configs": other}
         if cb is not None:

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <vector>
 #include <cstdlib>
+#include <thread>
 
 namespace pl {
 static thread_local char g_err[512] = "";
@@ -514,8 +515,96 @@ static int hc_get(int slot, size_t bytes, void** out) {
   *out = g_hc.p[slot];
   return 0;
 }
+// ---- pageable host memory ------------------------------------------------------------------------------------------
+// A numpy caller (what the reference's Cython binding passes) hands over PAGEABLE memory; cudaMemcpyAsync then goes
+// through the driver's single-threaded bounce buffer at ~12 GB/s (measured: 2 M x 512 took as long as 8 M x 512 from
+// pinned buffers).  For such pointers the pipeline stages the rows itself: a ring of pinned 64 MB slots (allocated
+// once, cached like the device buffers), filled / drained by a few host threads while the DMA of the previous slot
+// and the GPU work of the previous chunk are in flight.
+constexpr int PG_SLOTS = 4;
+constexpr size_t PG_BYTES = (size_t)64 << 20;
+static struct PageRing {
+  void* p[PG_SLOTS] = {};
+  cudaEvent_t ev[PG_SLOTS] = {};
+  int next = 0;
+} g_pg;
+static int pg_init() {
+  for (int i = 0; i < PG_SLOTS; i++) {
+    if (!g_pg.p[i]) PL_CUDA(cudaHostAlloc(&g_pg.p[i], PG_BYTES, cudaHostAllocDefault));
+    if (!g_pg.ev[i]) PL_CUDA(cudaEventCreateWithFlags(&g_pg.ev[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+static void pg_free() {
+  for (int i = 0; i < PG_SLOTS; i++) {
+    if (g_pg.p[i]) cudaFreeHost(g_pg.p[i]);
+    if (g_pg.ev[i]) cudaEventDestroy(g_pg.ev[i]);
+    g_pg.p[i] = nullptr; g_pg.ev[i] = nullptr;
+  }
+}
+static bool is_pageable(const void* ptr) {
+  if (getenv("PL_HOST_NO_STAGING")) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  static const int nt = []() { unsigned h = std::thread::hardware_concurrency(); int t = h ? (int)h : 4; if (const char* e = getenv("PL_HOST_COPY_THREADS")) t = atoi(e); return t < 1 ? 1 : (t > 16 ? 16 : t); }();
+  if (bytes < ((size_t)4 << 20) || nt == 1) { memcpy(dst, src, bytes); return; }
+  const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; i++) {
+    const size_t o = (size_t)i * per;
+    if (o >= bytes) break;
+    const size_t len = (o + per > bytes) ? bytes - o : per;
+    th.emplace_back([=]() { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, len); });
+  }
+  memcpy(dst, src, per < bytes ? per : bytes);
+  for (auto& t : th) t.join();
+}
+// pageable host -> device, enqueued on `cs` piece by piece through the pinned ring (blocks the calling thread only for the
+// host-side copies; the DMA of a piece overlaps the host copy of the next one)
+static int pg_h2d(void* dst, const void* src, size_t bytes, cudaStream_t cs) {
+  int rc = pg_init();
+  if (rc) return rc;
+  for (size_t o = 0; o < bytes; o += PG_BYTES) {
+    const size_t len = bytes - o < PG_BYTES ? bytes - o : PG_BYTES;
+    const int k = g_pg.next; g_pg.next = (k + 1) % PG_SLOTS;
+    PL_CUDA(cudaEventSynchronize(g_pg.ev[k]));                 // the slot's previous DMA is done
+    par_memcpy(g_pg.p[k], static_cast<const char*>(src) + o, len);
+    PL_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + o, g_pg.p[k], len, cudaMemcpyHostToDevice, cs));
+    PL_CUDA(cudaEventRecord(g_pg.ev[k], cs));
+  }
+  return 0;
+}
+// device -> pageable host: the DMA of piece i+1 runs while piece i is copied out of its pinned slot; returns when the data
+// is in `dst` (the caller has already ordered `cs` behind the producer of `src`)
+static int pg_d2h(void* dst, const void* src, size_t bytes, cudaStream_t cs) {
+  int rc = pg_init();
+  if (rc) return rc;
+  int pend_k = -1; size_t pend_o = 0, pend_len = 0;
+  for (size_t o = 0; o < bytes; o += PG_BYTES) {
+    const size_t len = bytes - o < PG_BYTES ? bytes - o : PG_BYTES;
+    const int k = g_pg.next; g_pg.next = (k + 1) % PG_SLOTS;
+    PL_CUDA(cudaEventSynchronize(g_pg.ev[k]));
+    PL_CUDA(cudaMemcpyAsync(g_pg.p[k], static_cast<const char*>(src) + o, len, cudaMemcpyDeviceToHost, cs));
+    PL_CUDA(cudaEventRecord(g_pg.ev[k], cs));
+    if (pend_k >= 0) {
+      PL_CUDA(cudaEventSynchronize(g_pg.ev[pend_k]));
+      par_memcpy(static_cast<char*>(dst) + pend_o, g_pg.p[pend_k], pend_len);
+    }
+    pend_k = k; pend_o = o; pend_len = len;
+  }
+  if (pend_k >= 0) {
+    PL_CUDA(cudaEventSynchronize(g_pg.ev[pend_k]));
+    par_memcpy(static_cast<char*>(dst) + pend_o, g_pg.p[pend_k], pend_len);
+  }
+  return 0;
+}
+
 void pl_host_cache_free(void) {
   for (int i = 0; i < HC_SLOTS; i++) { if (g_hc.p[i]) cudaFree(g_hc.p[i]); g_hc.p[i] = nullptr; g_hc.cap[i] = 0; }
+  pg_free();
 }
 
 // Row-chunk count of the host pipeline: ~2 GiB of snapshots per chunk, at least 4 chunks above 512 MiB, and every
@@ -638,6 +727,7 @@ static int host_factor(const double* Ai, int64_t m, int64_t n) {
   EventList ev, evs;
   if ((rc = ev.init(C)) || (rc = evs.init(2))) return rc;
   cudaStream_t st = H.st, cs = H.cs, s2 = H.s2;
+  const bool pageable_in = is_pageable(Ai);
   double* Rs = at(H.aux, H.o_rs);
   double* R2 = at(H.aux, H.o_r2);
   // chunks arrive, get factored and turned into explicit Q_c while the next chunk is on the wire
@@ -646,13 +736,15 @@ static int host_factor(const double* Ai, int64_t m, int64_t n) {
     double* Vb = at(H.dVb, k.vb);
     const size_t bytes = (size_t)k.rows * n * 8;
     if (direct) {
-      PL_CUDA(cudaMemcpyAsync(Vb, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
+      if (pageable_in) { if ((rc = pg_h2d(Vb, Ai + k.r0 * n, bytes, cs))) return rc; }
+      else PL_CUDA(cudaMemcpyAsync(Vb, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
       PL_CUDA(cudaEventRecord(ev.e[c], cs));
       PL_CUDA(cudaStreamWaitEvent(st, ev.e[c], 0));
     } else {
       double* sg = reinterpret_cast<double*>(static_cast<char*>(stage) + (size_t)(c & 1) * H.chunk_out);
       if (c >= 2) PL_CUDA(cudaStreamWaitEvent(cs, evs.e[c & 1], 0));         // staging buffer consumed
-      PL_CUDA(cudaMemcpyAsync(sg, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
+      if (pageable_in) { if ((rc = pg_h2d(sg, Ai + k.r0 * n, bytes, cs))) return rc; }
+      else PL_CUDA(cudaMemcpyAsync(sg, Ai + k.r0 * n, bytes, cudaMemcpyHostToDevice, cs));
       PL_CUDA(cudaEventRecord(ev.e[c], cs));
       PL_CUDA(cudaStreamWaitEvent(st, ev.e[c], 0));
       if ((rc = copy_pad(Vb, k.P.npad, sg, n, k.rows, n, k.P.npad, st))) return rc;
@@ -685,6 +777,7 @@ static int host_apply(double* Ui, const double* Wd) {
   int rc;
   EventList ev, evd;
   if ((rc = ev.init(C)) || (rc = evd.init(2))) return rc;
+  const bool pageable_out = is_pageable(Ui);
   const double* B = Wd;
   if (C > 1) {
     void* ws2 = static_cast<char*>(H.aux) + H.o_ws2;
@@ -703,9 +796,25 @@ static int host_apply(double* Ui, const double* Wd) {
     if ((rc = pad_small(Bp, H.kp, H.np, B + (size_t)c * n * n, n, n, n, nullptr, st))) return rc;
     if ((rc = gemm_tall(out, n, at(H.dVb, k.vb), k.P.npad, Bp, H.np, k.rows, n, H.kp, st))) return rc;
     PL_CUDA(cudaEventRecord(ev.e[c], st));
-    PL_CUDA(cudaStreamWaitEvent(cs, ev.e[c], 0));
-    PL_CUDA(cudaMemcpyAsync(Ui + k.r0 * n, out, (size_t)k.rows * n * 8, cudaMemcpyDeviceToHost, cs));
-    PL_CUDA(cudaEventRecord(evd.e[c & 1], cs));
+    if (!pageable_out) {
+      PL_CUDA(cudaStreamWaitEvent(cs, ev.e[c], 0));
+      PL_CUDA(cudaMemcpyAsync(Ui + k.r0 * n, out, (size_t)k.rows * n * 8, cudaMemcpyDeviceToHost, cs));
+      PL_CUDA(cudaEventRecord(evd.e[c & 1], cs));
+    } else {
+      // pageable destination: the previous chunk is drained through the pinned ring while this chunk's GEMM runs
+      // (the copy stream is still ordered behind the previous chunk's GEMM only)
+      if (c >= 1) {
+        HostChunk& kp = H.ch[c - 1];
+        double* outp = reinterpret_cast<double*>(static_cast<char*>(H.dOut) + (size_t)((c - 1) & 1) * H.chunk_out);
+        if ((rc = pg_d2h(Ui + kp.r0 * n, outp, (size_t)kp.rows * n * 8, cs))) return rc;
+        PL_CUDA(cudaEventRecord(evd.e[(c - 1) & 1], cs));
+      }
+      PL_CUDA(cudaStreamWaitEvent(cs, ev.e[c], 0));
+      if (c == C - 1) {
+        if ((rc = pg_d2h(Ui + k.r0 * n, out, (size_t)k.rows * n * 8, cs))) return rc;
+        PL_CUDA(cudaEventRecord(evd.e[c & 1], cs));
+      }
+    }
   }
   PL_CUDA(cudaStreamSynchronize(s2));
   PL_CUDA(cudaStreamSynchronize(st));

@@ -359,7 +359,7 @@ def parity_block(cx):
 
 
 # ---- other BASELINE configs as per-GPU shards ---------------------------------------------------------
-def other_config(cx, name, rows, n, kind, steps=3, warmup=2, m_global=None, seed=2025):
+def other_config(cx, name, rows, n, kind, steps=5, warmup=3, m_global=None, seed=2025):
     """Time one per-GPU shard; returns the dict that goes under other_configs[name]."""
     torch, pl = cx.torch, cx.pl
     size, rank, dev = cx.size, cx.rank, cx.dev
@@ -617,10 +617,10 @@ def run_ours(args):
             other["cfg3_shard_pod_24000000x256"] = other_config(cx, "cfg3", 24_000_000, 256, "POD.run(remove_mean=True)", seed=2023)
             other["cfg3_shard_pod_24000000x256"]["note"] = "1/8 of BASELINE configs[2] (64M points x 3 variables x 256 snapshots); with --gpus 8 the global matrix is config 3"
         if "cfg4" in want:
-            other["cfg4_shard_dmd_2000000x1000"] = other_config(cx, "cfg4", 2_000_000, 1000, "DMD.run", steps=2, warmup=1, seed=2024)
+            other["cfg4_shard_dmd_2000000x1000"] = other_config(cx, "cfg4", 2_000_000, 1000, "DMD.run", steps=3, warmup=3, seed=2024)
             other["cfg4_shard_dmd_2000000x1000"]["note"] = "1/8 of BASELINE configs[3] (16M x 1000): tsqr_svd of the first 999 snapshots + U^T Y2 (all-reduce) + reduced eig + modes"
         if "cfg1" in want and size == 1:
-            other["cfg1_pod_89351x151"] = other_config(cx, "cfg1", 89_351, 151, "POD.run(remove_mean=True)", steps=5, warmup=2, seed=2021)
+            other["cfg1_pod_89351x151"] = other_config(cx, "cfg1", 89_351, 151, "POD.run(remove_mean=True)", steps=10, warmup=3, seed=2021)
         if "strong" in want and size > 1:
             sc = other_config(cx, "strong", ROWS_PER_GPU // size, n, "tsqr_svd", m_global=ROWS_PER_GPU, seed=SEED)
             sc["note"] = f"strong-scaling reading of configs[1]: the SAME global 8,000,000 x 512 matrix split over {size} GPUs"

@@ -82,17 +82,26 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 }
 
 // Convergence state in device memory, so that the host never waits for a sweep (the call stays stream-ordered):
-//   st[0] rotations of the running sweep, st[1] grid-barrier counter (zeroed by a memset before every launch),
-//   st[2] converged flag, st[3] sweeps executed.
-// A fixed budget of sweep launches is enqueued; once a sweep ends without a rotation the remaining launches return
-// at once.  All rotations of a sweep are counted before its last grid barrier, so block 0 sees the final count.
+//   st[1] grid-barrier counter, st[2] converged flag, st[3] sweeps executed, st[4..6] rotation counters of three
+//   consecutive sweeps (rotating).
+// ALL sweeps run inside ONE cooperative launch (a launch per sweep had to win its SM slots back from the concurrently
+// running Q formation up to 40 times, most of them for an empty "already converged" launch).  Sweep s counts its
+// rotations in st[4 + s % 3]; every rotation is counted before the sweep's last grid barrier, so after it every CTA
+// reads the same final count and all of them leave the loop together.  Block 0 clears the counter of sweep s + 1 at
+// the start of sweep s: its last readers (end of sweep s - 2) have since arrived at a barrier of sweep s - 1, and its
+// next writers first pass a barrier of sweep s, which block 0 reaches after the store (fence inside grid_barrier).
 __device__ __forceinline__ bool sweep_done(const int* st) { return *reinterpret_cast<const volatile int*>(st + 2) != 0; }
-__device__ __forceinline__ void sweep_end(int* st) {
+__device__ __forceinline__ int* sweep_begin(int* st, int sweep) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) st[4 + (sweep + 1) % 3] = 0;
+  return st + 4 + sweep % 3;
+}
+__device__ __forceinline__ bool sweep_end(int* st, const int* cnt) {     // call after the last grid barrier of the sweep
+  const int nrot = *reinterpret_cast<const volatile int*>(cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (*reinterpret_cast<volatile int*>(st) == 0) st[2] = 1;
-    st[0] = 0;
     st[3] += 1;
+    if (nrot == 0) st[2] = 1;
   }
+  return nrot == 0;
 }
 // Not converged within the budget: poison S so that the failure is loud wherever the result is read.
 __global__ void jacobi_check_kernel(const int* st, double* S, int n) {
@@ -104,12 +113,16 @@ constexpr int JW = 8;   // warps (row pairs) per CTA
 
 template <int EPL>
 __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int ne,
-                                                               double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
-  if (sweep_done(rotations)) return;                        // converged in an earlier launch of the fixed sweep budget
+                                                               double tol, int* __restrict__ state, unsigned* bar, const double* __restrict__ fl,
+                                                               int max_sweeps) {
+  if (sweep_done(state)) return;
   const double floor2 = fl[0];
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * JW + (threadIdx.x >> 5);       // pair index inside a round
   const bool have = i < ne / 2;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+  int* rotations = sweep_begin(state, sweep);
+  const unsigned bar_base = (unsigned)sweep * (unsigned)(ne - 1) * gridDim.x;
   for (int round = 0; round < ne - 1; round++) {
     int p = 0, q = 0;
     if (have) {
@@ -148,9 +161,10 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
         }
       }
     }
-    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
+    grid_barrier(bar, bar_base + (unsigned)(round + 1) * gridDim.x);
   }
-  sweep_end(rotations);
+  if (sweep_end(state, rotations)) break;
+  }
 }
 
 // Block one-sided Jacobi: a CTA owns a PAIR OF ROW BLOCKS (2*BR rows of G and of J, staged in shared
@@ -160,14 +174,18 @@ __global__ void __launch_bounds__(JW * 32) jacobi_sweep_kernel(double* __restric
 // pairs inside a block exactly once per sweep), later rounds rotate only the BR*BR cross pairs.
 template <int BR, int EPL>
 __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
-                                                                 double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
+                                                                 double tol, int* __restrict__ state, unsigned* bar, const double* __restrict__ fl,
+                                                                 int max_sweeps) {
   extern __shared__ __align__(16) double jsm[];
-  if (sweep_done(rotations)) return;      // converged in an earlier launch of the fixed sweep budget
+  if (sweep_done(state)) return;
   const double floor2 = fl[0];
   double* Gs = jsm;                       // [2*BR][n]
   double* Js = jsm + (size_t)2 * BR * n;  // [2*BR][n]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i = blockIdx.x;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+  int* rotations = sweep_begin(state, sweep);
+  const unsigned bar_base = (unsigned)sweep * (unsigned)(nbe - 1) * gridDim.x;
   for (int round = 0; round < nbe - 1; round++) {
     int bp, bq;
     if (i == 0) { bp = nbe - 1; bq = round; }
@@ -247,9 +265,10 @@ __global__ void __launch_bounds__(256) jacobi_block_sweep_kernel(double* __restr
         }
       }
     }
-    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
+    grid_barrier(bar, bar_base + (unsigned)(round + 1) * gridDim.x);
   }
-  sweep_end(rotations);
+  if (sweep_end(state, rotations)) break;
+  }
 }
 
 // Block one-sided Jacobi, second generation: only G is staged in shared memory.  The left rotations of a block round are
@@ -287,15 +306,19 @@ __device__ __forceinline__ void jacobi_rotation(double a, double b, double c, do
 
 template <int BR, int EPL>
 __global__ void __launch_bounds__(256) jacobi_block_sweep2_kernel(double* __restrict__ Gm, double* __restrict__ J, int n, int nbe,
-                                                                  double tol, int* __restrict__ rotations, unsigned* bar, const double* __restrict__ fl) {
+                                                                  double tol, int* __restrict__ state, unsigned* bar, const double* __restrict__ fl,
+                                                                  int max_sweeps) {
   extern __shared__ __align__(16) double jsm[];
-  if (sweep_done(rotations)) return;      // converged in an earlier launch of the fixed sweep budget
+  if (sweep_done(state)) return;
   constexpr int R2 = 2 * BR, LDO = R2 + 1;
   const double floor2 = fl[0], tol2 = tol * tol;
   double* Gs = jsm;                       // [R2][n]
   double* Om = jsm + (size_t)R2 * n;      // [R2][LDO]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i = blockIdx.x;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+  int* rotations = sweep_begin(state, sweep);
+  const unsigned bar_base = (unsigned)sweep * (unsigned)(nbe - 1) * gridDim.x;
   for (int round = 0; round < nbe - 1; round++) {
     int bp, bq;
     if (i == 0) { bp = nbe - 1; bq = round; }
@@ -381,9 +404,10 @@ __global__ void __launch_bounds__(256) jacobi_block_sweep2_kernel(double* __rest
         J[(int64_t)gr * n + j] = acc0 + acc1;
       }
     }
-    grid_barrier(bar, (unsigned)(round + 1) * gridDim.x);
+    grid_barrier(bar, bar_base + (unsigned)(round + 1) * gridDim.x);
   }
-  sweep_end(rotations);
+  if (sweep_end(state, rotations)) break;
+  }
 }
 
 __global__ void __launch_bounds__(128) row_norm_kernel(double* s, const double* Gm, int n, int64_t ld) {
@@ -528,7 +552,7 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
   count_launches(2);
   const double tol = 2.0 * std::sqrt((double)n) * 2.220446049250313e-16;
   int sweeps = 0;
-  int* state = rot;                           // {rotations, barrier counter, converged, sweeps executed}
+  int* state = rot;                           // {-, barrier counter, converged, sweeps executed, 3 rotation counters, -}
   unsigned* bar = reinterpret_cast<unsigned*>(rot + 1);
   bool async_path = false;
   if (ni > 1) {
@@ -573,23 +597,27 @@ int svd_small(double* Ur, int64_t ldu, double* S, double* VT, int64_t ldvt, cons
         else PL_CUDA(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
       }
     }
-    PL_CUDA(cudaMemsetAsync(state, 0, 4 * sizeof(int), st));
+    PL_CUDA(cudaMemsetAsync(state, 0, 8 * sizeof(int), st));
     if (br || use_coop) {
-      // Stream-ordered: a fixed budget of sweeps is enqueued, convergence is tracked on the device (no host sync).
+      // Stream-ordered: ONE cooperative launch runs sweeps until one ends without a rotation (at most `budget`);
+      // convergence is tracked on the device (no host sync).  PL_JACOBI_MULTILAUNCH=1: one launch per sweep (A/B timing).
       async_path = true;
       static const int budget = getenv("PL_JACOBI_SWEEPS") ? atoi(getenv("PL_JACOBI_SWEEPS")) : 40;
-      for (int k = 0; k < budget; k++) {
-        if (k) PL_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+      static const bool multi = getenv("PL_JACOBI_MULTILAUNCH") != nullptr;
+      const int launches = multi ? budget : 1;
+      int per_launch = multi ? 1 : budget;
+      for (int k = 0; k < launches; k++) {
+        if (k) { PL_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st)); PL_CUDA(cudaMemsetAsync(state + 4, 0, 3 * sizeof(int), st)); }
         double tol_ = tol; int ni_ = ni, nbe_ = nbe, ne_ = ne;
         if (br) {
-          void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &state, &bar, &fl};
+          void* args[] = {&Gm, &J, &ni_, &nbe_, &tol_, &state, &bar, &fl, &per_launch};
           PL_CUDA(cudaLaunchCooperativeKernel(bfn, dim3(nbe / 2), dim3(256), args, bsm, st));
         } else {
-          void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &state, &bar, &fl};
+          void* args[] = {&Gm, &J, &ni_, &ne_, &tol_, &state, &bar, &fl, &per_launch};
           PL_CUDA(cudaLaunchCooperativeKernel(sweep_fn, dim3(sweep_blocks), dim3(JW * 32), args, 0, st));
         }
       }
-      count_launches(budget);
+      count_launches(launches);
     } else {
       // n > 1024 (or no cooperative launch): one launch per round and a host check per sweep.  This rare path
       // synchronises the stream.

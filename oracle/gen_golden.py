@@ -192,15 +192,47 @@ def main_dmd(outdir):
         print(name, blob["P1_muReal"][:4], blob["P1_muImag"][:4], os.path.getsize(path) // 1024, "KiB")
 
 
+# complex128 and float32 tsqr_svd: the reference's Python tsqr_svd is dtype-generic (numpy qr / svd), so the same
+# unmodified file yields the fixtures for the ztsqr_svd / stsqr_svd variants (pyLOM/vmmath/src/svd.c:955-1010, 529-563).
+DTYPE_CASES = [
+    # name, m, n, dtype, seed, ranks, decay (column j scaled by 10^(-decay j / n))
+    ("ztsqr_svd_500x12", 500, 12, np.complex128, 5, (1, 2, 3), 3.0),
+    ("stsqr_svd_800x20", 800, 20, np.float32, 6, (1, 2), 2.0),
+]
+
+
+def main_dtypes(outdir):
+    outdir = os.path.join(outdir, "aux")
+    os.makedirs(outdir, exist_ok=True)
+    for name, m, n, dt, seed, ranks, decay in DTYPE_CASES:
+        rng = np.random.default_rng(seed)
+        A = rng.standard_normal((m, n))
+        if dt == np.complex128:
+            A = A + 1j * rng.standard_normal((m, n))
+        A = np.ascontiguousarray((A * 10.0 ** (-decay * np.arange(n) / n)).astype(dt))
+        blob = {"A": A}
+        for P in ranks:
+            r = run_ranks(lambda ref, Ai: ref.svd.tsqr_svd(np.ascontiguousarray(Ai)), split_rows(A, P))
+            blob[f"P{P}_U"] = np.vstack([x[0] for x in r])
+            blob[f"P{P}_S"], blob[f"P{P}_V"] = r[0][1], r[0][2]
+            assert blob[f"P{P}_U"].dtype == dt and all(np.array_equal(x[1], r[0][1]) for x in r)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, blob["P1_S"][:3], blob["P1_U"].dtype, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     outdir = os.path.join(HERE, "..", "tests", "golden")
     if "--dmd" in sys.argv:
         return main_dmd(outdir)
+    if "--dtypes" in sys.argv:         # complex128 / float32 fixtures under tests/golden/aux/
+        return main_dtypes(outdir)
     os.makedirs(outdir, exist_ok=True)
     if "--rsvd" in sys.argv:           # only the randomized fixtures (leaves the others untouched)
         return main_rsvd(outdir)
     main_rsvd(outdir)
     main_dmd(outdir)
+    main_dtypes(outdir)
     for name, m, n, kind, seed, ranks in CASES:
         A = make_input(m, n, kind, seed)
         blob = {"A": A}

@@ -277,6 +277,35 @@ def test_complex_tsqr_svd(pl, case):
         assert np.abs(np.einsum("ik,ik->k", Uo.conj(), U)).min() >= 1 - 1e-8
 
 
+def test_complex_and_float32_against_reference_fixtures(pl):
+    """tests/golden/aux/{ztsqr_svd_500x12,stsqr_svd_800x20}.npz: outputs of the reference's own (dtype-generic) Python
+    tsqr_svd on complex128 / float32 input (oracle/gen_golden.py --dtypes; the C twins are ztsqr_svd / stsqr_svd,
+    pyLOM/vmmath/src/svd.c:955-1010, 529-563).  complex128: singular values to 1e-12, modes up to a unit complex factor.
+    float32: results come back as float32; tolerances are single-precision ones (the reference computed in float32)."""
+    aux = os.path.join(os.path.dirname(__file__), "golden", "aux")
+    g = np.load(os.path.join(aux, "ztsqr_svd_500x12.npz"))
+    A, Ug, Sg, Vg = g["A"], g["P1_U"], g["P1_S"], g["P1_V"]
+    n = A.shape[1]
+    U, S, VH = [np.asarray(host(t)) for t in pl.math.tsqr_svd(torch.from_numpy(A).cuda())]
+    assert U.dtype == np.complex128 and S.dtype == np.float64 and VH.dtype == np.complex128
+    assert np.abs(S - Sg).max() <= 1e-12 * Sg[0]
+    assert np.abs(np.einsum("ik,ik->k", Ug.conj(), U)).min() >= 1 - 1e-8
+    assert np.abs(np.einsum("kj,kj->k", Vg.conj(), VH)).min() >= 1 - 1e-8
+    assert np.abs((U * S) @ VH - A).max() <= 1e-11 * np.abs(A).max()
+    assert np.abs(U.conj().T @ U - np.eye(n)).max() <= 1e-10
+    g = np.load(os.path.join(aux, "stsqr_svd_800x20.npz"))
+    A, Ug, Sg, Vg = g["A"], g["P1_U"].astype(np.float64), g["P1_S"].astype(np.float64), g["P1_V"].astype(np.float64)
+    n = A.shape[1]
+    out = pl.math.tsqr_svd(torch.from_numpy(A).cuda())
+    assert all(t.dtype == torch.float32 for t in out)
+    U, S, V = [np.asarray(host(t), dtype=np.float64) for t in out]
+    assert np.abs(S - Sg).max() <= 1e-6 * Sg[0]
+    assert np.abs(np.einsum("ik,ik->k", Ug, U)).min() >= 1 - 1e-5
+    assert np.abs(np.einsum("kj,kj->k", Vg, V)).min() >= 1 - 1e-5
+    assert np.abs((U * S) @ V - A).max() <= 1e-5 * np.abs(A).max()
+    assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-5
+
+
 def test_exactly_rank_deficient_input(pl):
     """All-zero trailing snapshot columns give exactly zero singular values; U and V must stay orthonormal
     (LAPACK returns an arbitrary orthonormal completion, so only the invariants are compared)."""

@@ -92,6 +92,35 @@ def test_truncation_rule_matches_golden(golden_dir):
             assert compute_truncation_residual(torch.from_numpy(S), float(r)) == int(N)
 
 
+def test_complex_pair_selection_against_reference_golden(golden_dir):
+    """Host half of the complex tsqr_svd (vmmath/svd.py:_complex_select): the SVD of the real embedding
+    [[Ar, -Ai], [Ai, Ar]] (here by LAPACK, on the GPU by the Jacobi kernel) holds every complex singular triplet twice;
+    the selection must return the reference's singular values and right vectors (up to a unit complex factor per mode)
+    for the fixture made by the reference's own Python tsqr_svd, and for coinciding / zero singular values."""
+    from pyloworder_b200.vmmath.svd import _complex_select
+    g = np.load(os.path.join(golden_dir, "aux", "ztsqr_svd_500x12.npz"))
+    rng = np.random.default_rng(3)
+    n = 12
+    Q, _ = np.linalg.qr(rng.standard_normal((200, n)) + 1j * rng.standard_normal((200, n)))
+    W, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    sv = np.linspace(3.0, 1.0, n); sv[3] = sv[2]; sv[8] = sv[7] = sv[6]; sv[-2:] = 0.0
+    for A, Sref, VHref in ((g["A"], g["P1_S"], g["P1_V"]), ((Q * sv) @ W.conj().T, np.sort(sv)[::-1], None)):
+        Ahat = np.block([[A.real, -A.imag], [A.imag, A.real]])
+        U2, S2, V2 = np.linalg.svd(Ahat, full_matrices=False)
+        J, M, X = _complex_select(S2, V2, n)
+        assert len(J) == n and len(set(J.tolist())) == n
+        assert np.abs(S2[J] - Sref).max() <= 1e-13 * Sref[0]
+        VH = X.conj().T
+        assert np.abs(VH @ VH.conj().T - np.eye(n)).max() <= 1e-12
+        Uc = (U2[:A.shape[0], J] + 1j * U2[A.shape[0]:, J])
+        if M is not None:
+            Uc = Uc @ M
+        assert np.abs((Uc * S2[J]) @ VH - A).max() <= 1e-12 * np.abs(A).max() * n
+        if VHref is not None:      # separated spectrum: rows of V^H equal the reference's up to a phase
+            assert M is None
+            assert np.abs(np.einsum("kj,kj->k", VHref.conj(), VH)).min() >= 1 - 1e-10
+
+
 def test_bench_generator_matches_oracle_generator():
     sys.path.insert(0, ROOT)
     import bench, synth

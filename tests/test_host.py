@@ -121,6 +121,35 @@ def test_complex_pair_selection_against_reference_golden(golden_dir):
             assert np.abs(np.einsum("kj,kj->k", VHref.conj(), VH)).min() >= 1 - 1e-10
 
 
+def test_division_free_jacobi_rotation_formula():
+    """Executable spec of `jacobi_rotation` (csrc/svd_small.cu): t = sgn(d) h / (|d| + sqrt(d^2 + h^2)) with d = b - a,
+    h = 2 c is the textbook rotation t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 c), including the
+    sign conventions at d = +-0 and c < 0 (the kernel evaluates it with rsqrt / rcp seeds + Newton steps)."""
+    def lib(a, b, c):
+        d, h = b - a, 2.0 * c
+        den = abs(d) + np.sqrt(d * d + h * h)
+        t = (-h if np.signbit(d) else h) / den
+        cs = 1.0 / np.sqrt(1.0 + t * t)
+        return cs, cs * t
+    def book(a, b, c):
+        zeta = (b - a) / (2.0 * c)
+        t = np.copysign(1.0, zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta))
+        cs = 1.0 / np.sqrt(1.0 + t * t)
+        return cs, cs * t
+    rng = np.random.default_rng(0)
+    cases = [(1.0, 1.0, 0.3), (1.0, 1.0, -0.3), (2.0, 1.0, 0.5), (1.0, 2.0, -0.5), (1e-8, 1e8, 1e-3), (1e8, 1e-8, -1e-3)]
+    for _ in range(5000):
+        a, b = rng.random(2) * 10.0 ** rng.uniform(-3, 3, 2)
+        cases.append((a, b, rng.standard_normal() * np.sqrt(a * b) * rng.random()))
+    for a, b, c in cases:
+        if c == 0.0:
+            continue
+        (c1, s1), (c2, s2) = lib(a, b, c), book(a, b, c)
+        assert abs(c1 - c2) <= 4e-16 and abs(s1 - s2) <= 4e-16, (a, b, c)
+        # the rotation annihilates the inner product: rows x, y with |x|^2 = a, |y|^2 = b, x.y = c
+        assert abs((c1 * c1 - s1 * s1) * c + c1 * s1 * (a - b)) <= 1e-14 * max(a, b)
+
+
 def test_bench_generator_matches_oracle_generator():
     sys.path.insert(0, ROOT)
     import bench, synth
